@@ -1,0 +1,159 @@
+/*
+ * sparc_b200.h -- C ABI of libsparc_b200.so, the B200 (sm_100a) drop-in for the
+ * SPARC-AMP + outer-LDPC decode path of Spimp/sparc_ldpc.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) The reference's own FFI, unchanged (ldpc/src/c_ldpc.c, bound by
+ *      ldpc/py/ldpc.py:859-943 through ctypes.CDLL('./bin/c_ldpc.so')):
+ *      sumprod, sumprod2, minsum, Lxor, Lxfb -- HOST pointers, one codeword.
+ *      Pointing ldpc.py at this library instead of c_ldpc.so needs no other change
+ *      (see INTEGRATION.md).
+ *
+ *  (2) Batched, device-pointer entry points (prefix sb_) that replace the Python /
+ *      numpy hot path (ldpc/sparc_ldpc.py:32-356, ldpc/amp_exit.py:56-122,:272-305)
+ *      and the per-codeword ctypes call.  Every array argument of an sb_*_batch
+ *      function is a DEVICE pointer unless its name ends in _host; `stream` is a
+ *      cudaStream_t passed as void* (NULL = legacy default stream).  Layouts are
+ *      row-major, codeword-major: x[b][i].
+ *
+ * Conventions: all functions return >= 0 on success and a negative SB_E* code on
+ * failure, never throw, never call exit().  sb_last_error() returns a thread-local
+ * message for the last failure.  `long` is 64-bit (LP64), as the reference assumes
+ * (numpy int64 passed as c_long, ldpc.py:870-872).
+ */
+#ifndef SPARC_B200_H
+#define SPARC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK 0
+#define SB_EINVAL (-2)   /* bad argument / unsupported shape            */
+#define SB_ECUDA (-3)    /* CUDA runtime error (see sb_last_error())     */
+#define SB_ENOMEM (-1)   /* allocation failure (the reference's only error code, c_ldpc.c:165-166) */
+
+#define SB_MAX_ITCOUNT 200 /* ldpc/src/c_ldpc.c:7 */
+
+/* decode rules of sb_bp_batch */
+#define SB_BP_SUMPROD2 0 /* c_ldpc.c:138-206 (default of ldpc.py:855)  */
+#define SB_BP_SUMPROD 1  /* c_ldpc.c:32-113  (tanh / atanh rule)        */
+#define SB_BP_MINSUM 2   /* c_ldpc.c:339-381 (without the :364 indexing bug) */
+
+/* per-codeword status bits written by sb_amp_batch into flags[b] */
+#define SB_AMP_STOPPED 1u   /* tau == last_tau fired (sparc_ldpc.py:204)                        */
+#define SB_AMP_REF_NAN 2u   /* the reference's global-max softmax (sparc_ldpc.py:216-219) would
+                               have produced 0/0 in at least one section on this codeword        */
+
+const char *sb_last_error(void);
+int sb_version(void);
+/* number of kernels launched by this library since load / since the last reset (all threads) */
+long sb_launch_count(void);
+void sb_launch_count_reset(void);
+
+/* ------------------------------------------------------------------ (1) reference FFI
+ * Replaces ldpc/src/c_ldpc.c:32 / :138 / :339 / :234 / :294 symbol for symbol.
+ * Return value of the decoders: iterations used (0..200), -1 on allocation failure.
+ * `app` (length Nv) is fully overwritten; the caller owns every buffer. */
+int sumprod(double *ch, long *vdeg, long *cdeg, long *intrlv, int Nv, int Nc, int Nmsg, double *app);
+int sumprod2(double *ch, long *vdeg, long *cdeg, long *intrlv, int Nv, int Nc, int Nmsg, double *app);
+int minsum(double *ch, long *vdeg, long *cdeg, long *intrlv, int Nv, int Nc, int Nmsg, double *app,
+           double correction_factor);
+double Lxor(double L1, double L2, int corr_flag);
+double Lxfb(double *L, long dc, int corr_flag); /* overwrites L[0..dc) with extrinsics, returns the total */
+
+/* ------------------------------------------------------------------ (2a) Tanner graph handle
+ * Built once per code from the arrays ldpc.py:694-786 (prepare_decoder) returns. */
+typedef struct sb_graph sb_graph;
+int sb_graph_create(const long *vdeg_host, const long *cdeg_host, const long *intrlv_host, int Nv, int Nc, int Nmsg,
+                    sb_graph **out);
+void sb_graph_destroy(sb_graph *g);
+
+/* Batched flooding BP, one CTA per codeword, messages resident in shared memory.
+ * ch[B][Nv] in, app[B][Nv] out, it[B] out (iteration index at which every check was
+ * satisfied, or max_it).  Replaces ldpc.py:855-930 -> c_ldpc.c:138-206. */
+int sb_bp_batch(const sb_graph *g, int rule, const double *ch, int B, double *app, int *it, int max_it,
+                double minsum_factor, void *stream);
+
+/* ------------------------------------------------------------------ (2b) SPARC design operator
+ * Block sub-sampled Walsh-Hadamard operator of sparc_ldpc.py:81-147, built from the
+ * (L, n) uint32 `ordering` table sparc_transforms returns (host pointer). */
+typedef struct sb_operator sb_operator;
+int sb_operator_create(const uint32_t *ordering_host, int L, int M, int n, sb_operator **out);
+void sb_operator_destroy(sb_operator *op);
+
+/* out[b][0..n) = A_S beta[b] where S = the codeword's section list (sparc_ldpc.py:143-144;
+ * sparc_transforms_shorter :154-168 when `sections` is given).  beta[b] is compact:
+ * nsec[b]*M entries.  sections == NULL: all L sections in order; nsec == NULL: L. */
+int sb_Ab_batch(const sb_operator *op, const double *beta, const int *sections, const int *nsec, int B, double *out,
+                void *stream);
+/* out[b][0..nsec*M) = A_S^T z[b]  (sparc_ldpc.py:145-146) */
+int sb_Az_batch(const sb_operator *op, const double *z, const int *sections, const int *nsec, int B, double *out,
+                void *stream);
+
+/* out[b][k] = (y ? y[b][k] : 0) + sign * sum_l sqrt(n*Pl[l]) * A[k, l*M + idx[b][l]]   over sections with idx >= 0.
+ * The SPARC encoder (sparc_ldpc.py:436-439, sign=+1, y=NULL) and the peeling subtraction
+ * (sparc_ldpc.py:508-518, amp_exit.py:111-112, sign=-1). */
+int sb_onehot_apply_batch(const sb_operator *op, const int *idx, const double *Pl, const double *y, double sign, int B,
+                          double *out, void *stream);
+
+/* AMP decoder, sparc_ldpc.py:189-222 / amp_test.py:14-50, one persistent CTA per codeword.
+ *   y[B][n]; Pl[L] (indexed by section id); beta0[B][L*M] or NULL (zero start);
+ *   sections[B][L] / nsec[B] or NULL (all sections): active-section lists, beta is compact;
+ *   beta[B][L*M] out; iters[B] out = the `t` amp_test returns; n_exec[B] out = iterations
+ *   actually executed; flags[B] out (SB_AMP_*); tau2_trace[B][T] or NULL. */
+int sb_amp_batch(const sb_operator *op, const double *y, const double *Pl, const double *beta0, const int *sections,
+                 const int *nsec, int B, int T, double *beta, int *iters, int *n_exec, unsigned *flags,
+                 double *tau2_trace, void *stream);
+
+/* ------------------------------------------------------------------ (2c) section <-> bit handoff
+ * p = sp2bp(beta / sqrt(n*Pl)) (sparc_ldpc.py:257-281, :657); llr = nan_to_num(log(1-p) - log(p)) (:667-669).
+ * beta rows have stride `beta_stride` doubles.  Codeword b processes a list of sections:
+ *   sections == NULL: entries i = 0..count-1, section id s = first_sec + i (indexes Pl),
+ *                     beta block (beta_first + i), output bits at (out_first + i)*logM ..;
+ *   sections != NULL: entries i = 0..nsec[b]-1, s = sections[b][i] (row stride L_stride ints),
+ *                     beta block (beta_first + i), output bits at s*logM .. (sparc_ldpc.py:1031-1034).
+ * p and llr rows have stride `out_stride` doubles; p may be NULL. */
+int sb_sp2bp_llr_batch(const double *beta, long beta_stride, int beta_first, const int *sections, const int *nsec,
+                       int L_stride, int first_sec, int out_first, int count, int M, int n, const double *Pl, int B,
+                       double *p, double *llr, long out_stride, void *stream);
+
+/* Section priors / posteriors from bit information (sparc_ldpc.py:283-314, :685-696).  in[B][ls*logM] holds the
+ * LDPC a-posteriori LLRs (bit posterior 1/(1+exp(app)), :685) or, with SB_PRIOR_FROM_PROB, bit probabilities.
+ * Protected sections [L-ls, L) get bp2sp(bits); unprotected sections get beta_prev/sqrt(n*Pl) (:657).  With
+ * SB_PRIOR_SCALE every section is then multiplied by sqrt(n*Pl) to give the next AMP initialisation (:696). */
+#define SB_PRIOR_SCALE 1
+#define SB_PRIOR_FROM_PROB 2
+int sb_bp2sp_prior_batch(const double *in, int ls, const double *beta_prev, int L, int M, int n, const double *Pl,
+                         int mode, int B, double *out, void *stream);
+
+/* idx[b][i] = argmax of section i of beta[b] (first maximum wins, sparc_ldpc.py:640-643) */
+int sb_argmax_batch(const double *beta, long beta_stride, int count, int M, int B, int *idx, long idx_stride,
+                    void *stream);
+/* idx[b][i] = MSB-first index of hard decisions (llr < 0) (sparc_ldpc.py:317-341, :352, :672-674) */
+int sb_llr2idx_batch(const double *llr, long llr_stride, int count, int M, int B, int *idx, long idx_stride,
+                     void *stream);
+/* errs[b] = sum_i popcount(a[b][i] ^ t[b][i]) (sparc_ldpc.py:650) */
+int sb_count_errors_batch(const int *a, const int *t, int count, int B, int *errs, void *stream);
+
+/* beta[b][l*M + idx[b][l]] = sqrt(n*Pl[l]), zero elsewhere (sparc_ldpc.py:840-843); idx < 0: all-zero section */
+int sb_onehot_beta_batch(const int *idx, const double *Pl, int n, int L, int M, int B, double *beta, void *stream);
+
+/* Threshold peel (amp_exit.py:85-116): post[B][L*M] section posteriors; sections l >= L-ls with exactly one
+ * entry > threshold are hard decided.  hard_idx[B][L] = decided index or -1; act[B][L] = ascending list of the
+ * remaining sections, nact[B] its length. */
+int sb_threshold_peel_batch(const double *post, int L, int M, int ls, double threshold, int B, int *hard_idx,
+                            int *act, int *nact, void *stream);
+
+/* EXIT histograms (amp_exit.py:299-305): counts[b][0][.] for X == +1 and counts[b][1][.] for X == -1 of E[b][.]
+ * over the nbins = nedges-1 bins delimited by edges[] (numpy.histogram semantics: left-closed, last bin closed). */
+int sb_exit_hist_batch(const double *E, const int *X, int len, const double *edges, int nedges, int B,
+                       long long *counts, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARC_B200_H */

@@ -1,0 +1,528 @@
+// amp.cu -- SPARC design operator and AMP decoder kernels (sm_100a, fp64).
+//
+// Replaces ldpc/sparc_ldpc.py:32-147 (sub_fht / block_sub_fht / sparc_transforms[_shorter]) and
+// :189-222 (amp) of the reference.  The reference zero-pads every section to w = 2^ceil(log2(n+1))
+// and runs a w-point Walsh-Hadamard transform; because only the last M columns of H_w are used,
+//     (A beta)[k]  = (1/sqrt n) sum_l sgn(l,k) * FHT_M(beta_l)[lo(l,k)]
+//     (A^T z)_l    = (1/sqrt n) FHT_M(fold_l(z)),
+// with r = ordering[l][k], lo = r mod M, hi = r div M, sgn = (-1)^popcount(hi) and fold_l the signed
+// butterfly tree over the w/M blocks.  Both identities are exact in floating point when the adds are
+// done in the reference's order, which these kernels do: the fold tree is evaluated in the order of the
+// large-stride butterflies, the M-point stages run from stride M/2 down to 1, and sections are
+// accumulated into A beta in ascending order (sparc_ldpc.py:123-126).
+//
+// Kernel structure: ONE persistent CTA per codeword runs the whole AMP loop (all T iterations) in a
+// single launch.  z and the A beta accumulator live in shared memory; beta streams through HBM once in
+// and once out per iteration (section-wise softmax needs only the section itself); the two lookup
+// tables (fwd: u16 [L][n], inv: u16 [L][M][Hp]) are shared by the whole batch and stay L2-resident.
+#include "common.cuh"
+
+namespace sb {
+
+template <int LOGM>
+struct TeamCfg {
+    static constexpr int M = 1 << LOGM;
+    static constexpr int TEAM = (M >= 128) ? 32 : (M >= 4 ? M / 4 : 1);  // lanes cooperating on one section
+    static constexpr int EPT = M / TEAM;                                  // elements per lane
+};
+
+// shuffle mask of the calling lane's team (teams of one warp may diverge from each other)
+template <int TEAM>
+__device__ __forceinline__ unsigned team_mask() {
+    if constexpr (TEAM >= 32) {
+        return 0xffffffffu;
+    } else {
+        return ((1u << TEAM) - 1u) << (((threadIdx.x & 31) / TEAM) * TEAM);
+    }
+}
+
+// M-point Walsh-Hadamard transform of one section held by a team: element j = e*TEAM + q lives in
+// x[e] of team lane q.  Stage order = strides M/2 ... 1 (ldpc/sparc_ldpc.py:19-29): (a, b) -> (a+b, a-b).
+template <int LOGM>
+__device__ __forceinline__ void fht_team(double (&x)[TeamCfg<LOGM>::EPT], int q, unsigned tmask) {
+    constexpr int TEAM = TeamCfg<LOGM>::TEAM, EPT = TeamCfg<LOGM>::EPT;
+#pragma unroll
+    for (int s = EPT / 2; s >= 1; s >>= 1) {
+#pragma unroll
+        for (int i = 0; i < EPT; i++) {
+            if ((i & s) == 0) {
+                double a = x[i], b = x[i + s];
+                x[i] = a + b;
+                x[i + s] = a - b;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = TEAM / 2; d >= 1; d >>= 1) {
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            double p = __shfl_xor_sync(tmask, x[e], d);
+            x[e] = (q & d) ? (p - x[e]) : (x[e] + p);
+        }
+    }
+}
+
+// One bin of fold_l(z): NB blocks of 16 inverse-table entries in visit order; every tree node is
+// (left - right), i.e. v <- v[:half] - v[half:] of the reference's large-stride butterflies.
+__device__ __forceinline__ double fold_bin(const uint16_t *__restrict__ tab, int NB, const double *zs) {
+    double st[8];
+    double val = 0.0;
+    for (int c = 0; c < NB; c++) {
+        const uint4 p0 = __ldg(reinterpret_cast<const uint4 *>(tab + c * 16));
+        const uint4 p1 = __ldg(reinterpret_cast<const uint4 *>(tab + c * 16 + 8));
+        const uint32_t wds[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t k0 = wds[i] & 0xFFFFu, k1 = wds[i] >> 16;
+            v[2 * i] = (k0 == 0xFFFFu) ? 0.0 : zs[k0];
+            v[2 * i + 1] = (k1 == 0xFFFFu) ? 0.0 : zs[k1];
+        }
+#pragma unroll
+        for (int s = 1; s < 16; s <<= 1) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2 * s) v[i] = v[i] - v[i + s];
+        }
+        val = v[0];
+        if (NB > 1) {  // binary-counter merge of the block subtrees (left - right at every level)
+            int cc = c, lvl = 0;
+#pragma unroll
+            for (int l = 0; l < 7; l++) {
+                if (cc & 1) {
+                    val = st[l] - val;
+                    cc >>= 1;
+                    lvl = l + 1;
+                } else {
+                    break;
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < 8; l++)
+                if (l == lvl) st[l] = val;
+        }
+    }
+    return val;
+}
+
+struct AmpArgs {
+    const uint16_t *fwd, *inv;
+    const double *y, *Pl, *beta0;
+    const int *sections, *nsec;
+    double *beta, *tau2_trace;
+    int *iters, *n_exec;
+    unsigned *flags;
+    int L, n, Hp, NB, T;
+};
+
+// mode 0: AMP iteration (fold -> FHT -> softmax -> store beta -> FHT -> F)
+// mode 1: operator only (load beta -> FHT -> F)            [prologue z = y - A beta0, sb_Ab_batch]
+template <int LOGM>
+__device__ __forceinline__ void section_phase(int mode, bool first_zero, const AmpArgs &a, const double *bsrc,
+                                              double *bdst, int sec, int q, const double *zs, double *Fdst,
+                                              double inv_rt_n, double rt_npl, double tau2, double &sq, double &gmax,
+                                              double &lmin) {
+    constexpr int M = TeamCfg<LOGM>::M, TEAM = TeamCfg<LOGM>::TEAM, EPT = TeamCfg<LOGM>::EPT;
+    double x[EPT];
+    const unsigned tmask = team_mask<TEAM>();
+    if (mode == 0) {
+        const uint16_t *tab = a.inv + ((size_t)sec * M) * a.Hp;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) x[e] = fold_bin(tab + (size_t)(e * TEAM + q) * a.Hp, a.NB, zs);
+        fht_team<LOGM>(x, q, tmask);
+        const double c2 = rt_npl / tau2;
+        double m = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const double b = first_zero ? 0.0 : bsrc[e * TEAM + q];
+            const double s = b + x[e] * inv_rt_n;  // s = beta + A^T z          (sparc_ldpc.py:213)
+            x[e] = s * c2;                         // u = s sqrt(n P_l)/tau^2    (:215)
+            m = fmax(m, x[e]);
+        }
+#pragma unroll
+        for (int d = TEAM / 2; d >= 1; d >>= 1) m = fmax(m, __shfl_xor_sync(tmask, m, d));
+        gmax = fmax(gmax, m);
+        lmin = fmin(lmin, m);
+        double sum = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            x[e] = exp(x[e] - m);  // section max instead of the reference's global max (:216): same softmax
+            sum += x[e];
+        }
+#pragma unroll
+        for (int d = TEAM / 2; d >= 1; d >>= 1) sum += __shfl_xor_sync(tmask, sum, d);
+        const double sc = rt_npl / sum;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            x[e] *= sc;  // beta = sqrt(n P_l) softmax(u)    (:218-219)
+            sq += x[e] * x[e];
+            bdst[e * TEAM + q] = x[e];
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            x[e] = bsrc[e * TEAM + q];
+            if (bdst != nullptr) bdst[e * TEAM + q] = x[e];
+        }
+    }
+    fht_team<LOGM>(x, q, tmask);
+#pragma unroll
+    for (int e = 0; e < EPT; e++) Fdst[e * TEAM + q] = x[e];
+}
+
+// acc[k] += sum over the group's sections (ascending) of sgn * F[lo]     (sparc_ldpc.py:123-126, :70)
+__device__ __forceinline__ void gather_phase(const uint16_t *__restrict__ fwd, int n, int M, int nvalid,
+                                             const int *sec_s, const double *Fs, double *acc_s) {
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        double acc = acc_s[k];
+        for (int tm = 0; tm < nvalid; tm++) {
+            const uint32_t e = __ldg(fwd + (size_t)sec_s[tm] * n + k);
+            const double v = Fs[tm * M + (e & 0x7FFFu)];
+            acc += (e & 0x8000u) ? -v : v;
+        }
+        acc_s[k] = acc;
+    }
+}
+
+// One pass over all active sections: section_phase per team, then gather_phase per group.
+template <int LOGM>
+__device__ __forceinline__ void operator_pass(int mode, bool first_zero, const AmpArgs &a, const double *bsrc,
+                                              double *bdst, const int *act, int La, double *zs, double *acc_s,
+                                              double *Fs, int *sec_s, double inv_rt_n, double nd, double tau2,
+                                              double &sq, double &gmax, double &lmin) {
+    constexpr int M = TeamCfg<LOGM>::M, TEAM = TeamCfg<LOGM>::TEAM;
+    const int W = blockDim.x / TEAM;  // sections per group
+    const int tm = threadIdx.x / TEAM, q = threadIdx.x % TEAM;
+    for (int k = threadIdx.x; k < a.n; k += blockDim.x) acc_s[k] = 0.0;
+    for (int g0 = 0; g0 < La; g0 += W) {
+        const int sidx = g0 + tm;
+        const bool valid = sidx < La;
+        const int sec = valid ? (act ? act[sidx] : sidx) : 0;
+        if (q == 0 && tm < W) sec_s[tm] = sec;
+        if (valid) {
+            const double rt_npl = sqrt(nd * a.Pl[sec]);
+            section_phase<LOGM>(mode, first_zero, a, bsrc ? bsrc + (size_t)sidx * M : nullptr,
+                                bdst ? bdst + (size_t)sidx * M : nullptr, sec, q, zs, Fs + tm * M, inv_rt_n, rt_npl,
+                                tau2, sq, gmax, lmin);
+        }
+        __syncthreads();
+        const int nvalid = min(W, La - g0);
+        gather_phase(a.fwd, a.n, M, nvalid, sec_s, Fs, acc_s);
+        __syncthreads();
+    }
+}
+
+template <int LOGM>
+__global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a) {
+    constexpr int M = TeamCfg<LOGM>::M, TEAM = TeamCfg<LOGM>::TEAM;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, b = blockIdx.x;
+    const int W = blockDim.x / TEAM;
+    double *zs = reinterpret_cast<double *>(smem_raw);
+    double *acc_s = zs + n;
+    double *Fs = acc_s + n;
+    double *red = Fs + (size_t)W * M;  // 40 doubles
+    int *sec_s = reinterpret_cast<int *>(red + 40);
+
+    const int La = a.nsec ? a.nsec[b] : a.L;
+    const int *act = a.sections ? a.sections + (size_t)b * a.L : nullptr;
+    const double *y = a.y + (size_t)b * n;
+    double *beta = a.beta + (size_t)b * a.L * M;
+    const double nd = (double)n;
+    const double rt_n = sqrt(nd), inv_rt_n = 1.0 / rt_n;
+    double sq = 0.0, gmax = -INFINITY, lmin = INFINITY;
+
+    if (La <= 0) {  // the reference never calls amp() on an empty section set (sparc_ldpc.py:1015)
+        if (threadIdx.x == 0) {
+            a.iters[b] = 0;
+            a.n_exec[b] = 0;
+            a.flags[b] = 0;
+        }
+        return;
+    }
+
+    // P = sum of the active sections' power (np.sum(Pl), sparc_ldpc.py:190)
+    double pl = 0.0;
+    for (int i = threadIdx.x; i < La; i += blockDim.x) pl += a.Pl[act ? act[i] : i];
+    const double P = block_sum(pl, red);
+
+    if (a.beta0 != nullptr) {  // z = y - A beta0   (sparc_ldpc.py:197-198)
+        operator_pass<LOGM>(1, false, a, a.beta0 + (size_t)b * a.L * M, beta, act, La, zs, acc_s, Fs, sec_s, inv_rt_n,
+                            nd, 1.0, sq, gmax, lmin);
+        for (int k = threadIdx.x; k < n; k += blockDim.x) zs[k] = y[k] - acc_s[k] / rt_n;
+    } else {
+        for (int k = threadIdx.x; k < n; k += blockDim.x) zs[k] = y[k];
+    }
+    __syncthreads();
+
+    bool first_zero = (a.beta0 == nullptr);
+    double last_tau = 0.0;
+    unsigned flags = 0;
+    int t = 0, executed = 0;
+    for (t = 0; t < a.T; t++) {
+        double part = 0.0;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) part += zs[k] * zs[k];
+        const double tau = sqrt(block_sum(part, red) / nd);  // (:203)
+        if (tau == last_tau) {                               // exact-equality stop (:204)
+            flags |= SB_AMP_STOPPED;
+            break;
+        }
+        last_tau = tau;
+        const double tau2 = tau * tau;
+        if (a.tau2_trace != nullptr && threadIdx.x == 0) a.tau2_trace[(size_t)b * a.T + t] = tau2;
+        sq = 0.0;
+        gmax = -INFINITY;
+        lmin = INFINITY;
+        operator_pass<LOGM>(0, first_zero, a, beta, beta, act, La, zs, acc_s, Fs, sec_s, inv_rt_n, nd, tau2, sq, gmax,
+                            lmin);
+        first_zero = false;
+        const double sumsq = block_sum(sq, red);
+        const double gm = block_max(gmax, red);
+        const double lm = -block_max(-lmin, red);
+        if (gm - lm > 745.13) flags |= SB_AMP_REF_NAN;
+        const double ons = P - sumsq / nd;  // (:220)
+        for (int k = threadIdx.x; k < n; k += blockDim.x) zs[k] = (y[k] - acc_s[k] / rt_n) + (zs[k] / tau2) * ons;
+        __syncthreads();
+        executed++;
+    }
+    if (first_zero) {  // T == 0 or stop before the first update: beta is the zero vector
+        for (int i = threadIdx.x; i < La * M; i += blockDim.x) beta[i] = 0.0;
+    }
+    if (threadIdx.x == 0) {
+        a.iters[b] = (t < a.T) ? t : (a.T > 0 ? a.T - 1 : 0);
+        a.n_exec[b] = executed;
+        a.flags[b] = flags;
+    }
+}
+
+// A_S beta for a batch (sparc_ldpc.py:143-144): out = acc / sqrt(n)
+template <int LOGM>
+__global__ void __launch_bounds__(512, 1) Ab_kernel(AmpArgs a, const double *beta_in, double *out) {
+    constexpr int M = TeamCfg<LOGM>::M, TEAM = TeamCfg<LOGM>::TEAM;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, b = blockIdx.x;
+    const int W = blockDim.x / TEAM;
+    double *zs = reinterpret_cast<double *>(smem_raw);
+    double *acc_s = zs + n;
+    double *Fs = acc_s + n;
+    double *red = Fs + (size_t)W * M;
+    int *sec_s = reinterpret_cast<int *>(red + 40);
+    const int La = a.nsec ? a.nsec[b] : a.L;
+    const int *act = a.sections ? a.sections + (size_t)b * a.L : nullptr;
+    double sq = 0, gmax = 0, lmin = 0;
+    const double nd = (double)n, rt_n = sqrt(nd);
+    operator_pass<LOGM>(1, false, a, beta_in + (size_t)b * a.L * M, nullptr, act, La, zs, acc_s, Fs, sec_s, 1.0 / rt_n,
+                        nd, 1.0, sq, gmax, lmin);
+    for (int k = threadIdx.x; k < n; k += blockDim.x) out[(size_t)b * n + k] = acc_s[k] / rt_n;
+}
+
+// A_S^T z for a batch (sparc_ldpc.py:145-146): one team per section
+template <int LOGM>
+__global__ void __launch_bounds__(512, 1) Az_kernel(AmpArgs a, const double *z_in, double *out) {
+    constexpr int M = TeamCfg<LOGM>::M, TEAM = TeamCfg<LOGM>::TEAM, EPT = TeamCfg<LOGM>::EPT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, b = blockIdx.x;
+    const int W = blockDim.x / TEAM;
+    double *zs = reinterpret_cast<double *>(smem_raw);
+    const int La = a.nsec ? a.nsec[b] : a.L;
+    const int *act = a.sections ? a.sections + (size_t)b * a.L : nullptr;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) zs[k] = z_in[(size_t)b * n + k];
+    __syncthreads();
+    const double rt_n = sqrt((double)n);
+    const int tm = threadIdx.x / TEAM, q = threadIdx.x % TEAM;
+    for (int sidx = tm; sidx < La; sidx += W) {  // whole teams leave together: shuffles stay converged
+        const int sec = act ? act[sidx] : sidx;
+        double x[EPT];
+        const uint16_t *tab = a.inv + ((size_t)sec * M) * a.Hp;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) x[e] = fold_bin(tab + (size_t)(e * TEAM + q) * a.Hp, a.NB, zs);
+        fht_team<LOGM>(x, q, team_mask<TEAM>());
+#pragma unroll
+        for (int e = 0; e < EPT; e++) out[(size_t)b * a.L * M + (size_t)sidx * M + e * TEAM + q] = x[e] / rt_n;
+    }
+}
+
+// out[b][k] = y[b][k] + sign * (sum_l c_l * sgn(l,k) * H_M[lo(l,k), idx_l]) / sqrt(n): the transform of a one-hot
+// section is +-c exactly, so this equals the reference's Ab(beta_onehot) bit for bit (sections ascending).
+__global__ void onehot_kernel(const uint16_t *__restrict__ fwd, int L, int n, const int *__restrict__ idx,
+                              const double *__restrict__ Pl, const double *__restrict__ y, double sign,
+                              double *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *sidx = reinterpret_cast<int *>(smem_raw);
+    double *coef = reinterpret_cast<double *>(sidx + ((L + 1) & ~1));
+    const int b = blockIdx.y;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        sidx[l] = idx[(size_t)b * L + l];
+        coef[l] = sqrt((double)n * Pl[l]);
+    }
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double rt_n = sqrt((double)n);
+    double acc = 0.0;
+    for (int l = 0; l < L; l++) {
+        const int j = sidx[l];
+        if (j < 0) continue;
+        const uint32_t e = __ldg(fwd + (size_t)l * n + k);
+        const int neg = ((e >> 15) & 1) ^ (__popc((e & 0x7FFFu) & (uint32_t)j) & 1);
+        acc += neg ? -coef[l] : coef[l];
+    }
+    const double x = acc / rt_n;
+    const double base = y ? y[(size_t)b * n + k] : 0.0;
+    out[(size_t)b * n + k] = (sign < 0) ? (base - x) : (base + x);
+}
+
+static size_t amp_smem(int n, int M, int W) {
+    return sizeof(double) * ((size_t)2 * n + (size_t)W * M + 40) + sizeof(int) * (size_t)(W + 2);
+}
+
+static int pick_threads(int n, int M, int TEAM, int L) {
+    // 256 threads let two CTAs share an SM when shared memory allows; otherwise 512.
+    int nt = 256;
+    const char *env = getenv("SB_AMP_THREADS");
+    if (env) nt = atoi(env);
+    else if (2 * (amp_smem(n, M, 256 / TEAM) + 1024) > 227 * 1024) nt = 512;
+    if (nt < 32) nt = 32;
+    if (nt > 512) nt = 512;  // __launch_bounds__(512, 1)
+    nt = (nt / 32) * 32;
+    if (nt < TEAM) nt = TEAM;
+    // no point in more teams than sections
+    while (nt > 64 && (nt / 2) / TEAM >= L) nt /= 2;
+    return nt;
+}
+
+template <int LOGM>
+static int launch_amp(const sb_operator *op, AmpArgs a, int B, int which, const double *in, double *out,
+                      cudaStream_t st) {
+    constexpr int TEAM = TeamCfg<LOGM>::TEAM, M = TeamCfg<LOGM>::M;
+    const int nt = pick_threads(op->n, M, TEAM, op->L);
+    const size_t smem = amp_smem(op->n, M, nt / TEAM);
+    if (smem > 227 * 1024) return fail(SB_EINVAL, "AMP: n too large for shared memory%s (%ld bytes)", "", (long)smem);
+    if (which == 0) {
+        SB_CUDA(cudaFuncSetAttribute(amp_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        amp_kernel<LOGM><<<B, nt, smem, st>>>(a);
+    } else if (which == 1) {
+        SB_CUDA(cudaFuncSetAttribute(Ab_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        Ab_kernel<LOGM><<<B, nt, smem, st>>>(a, in, out);
+    } else {
+        SB_CUDA(cudaFuncSetAttribute(Az_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        Az_kernel<LOGM><<<B, nt, smem, st>>>(a, in, out);
+    }
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+static int dispatch(const sb_operator *op, AmpArgs a, int B, int which, const double *in, double *out,
+                    cudaStream_t st) {
+    switch (op->logM) {
+#define SB_CASE(l) \
+    case l:        \
+        return launch_amp<l>(op, a, B, which, in, out, st);
+        SB_CASE(1) SB_CASE(2) SB_CASE(3) SB_CASE(4) SB_CASE(5) SB_CASE(6) SB_CASE(7) SB_CASE(8) SB_CASE(9) SB_CASE(10)
+#undef SB_CASE
+    }
+    return fail(SB_EINVAL, "unsupported section size M = 2^%s%ld", "", op->logM);
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" int sb_operator_create(const uint32_t *ordering, int L, int M, int n, sb_operator **out) {
+    if (!ordering || !out || L <= 0 || n <= 0 || M < 2 || (M & (M - 1)) || M > 1024 || n >= 65535)
+        return fail(SB_EINVAL, "sb_operator_create: bad shape%s (M=%ld)", "", M);
+    int w = 1;
+    while (w < (M + 1 > n + 1 ? M + 1 : n + 1)) w <<= 1;  // sparc_ldpc.py:54,110
+    sb_operator *op = new sb_operator();
+    op->L = L; op->M = M; op->n = n; op->logM = ilog2(M); op->w = w;
+    op->H = w / M;
+    op->Hp = op->H < 16 ? 16 : op->H;
+    op->NB = op->Hp / 16;
+    if (op->NB > 128) { delete op; return fail(SB_EINVAL, "sb_operator_create: w/M too large%s (%ld)", "", op->H); }
+    const int logH = ilog2(op->H);
+    const size_t nf = (size_t)L * n, ni = (size_t)L * M * op->Hp;
+    uint16_t *hf = (uint16_t *)malloc(nf * 2), *hi = (uint16_t *)malloc(ni * 2);
+    if (!hf || !hi) { free(hf); free(hi); delete op; return fail(SB_ENOMEM, "sb_operator_create: host alloc%s", ""); }
+    memset(hi, 0xFF, ni * 2);
+    for (int l = 0; l < L; l++)
+        for (int k = 0; k < n; k++) {
+            const uint32_t r = ordering[(size_t)l * n + k];
+            if (r == 0 || r >= (uint32_t)w) { free(hf); free(hi); delete op; return fail(SB_EINVAL, "ordering entry out of [1,w)%s", ""); }
+            const uint32_t lo = r % M, hiw = r / M;
+            uint32_t c = 0;  // visit position = bit reversal of the block index over log2(H) bits
+            for (int bbit = 0; bbit < logH; bbit++) c |= ((hiw >> bbit) & 1u) << (logH - 1 - bbit);
+            hf[(size_t)l * n + k] = (uint16_t)(lo | ((__builtin_popcount(hiw) & 1) << 15));
+            hi[((size_t)l * M + lo) * op->Hp + c] = (uint16_t)k;
+        }
+    op->fwd = nullptr; op->inv = nullptr;
+    cudaError_t e1 = cudaMalloc(&op->fwd, nf * 2), e2 = cudaMalloc(&op->inv, ni * 2);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        cudaFree(op->fwd); cudaFree(op->inv); free(hf); free(hi); delete op;
+        return fail(SB_ENOMEM, "sb_operator_create: cudaMalloc failed%s", "");
+    }
+    e1 = cudaMemcpy(op->fwd, hf, nf * 2, cudaMemcpyHostToDevice);
+    e2 = cudaMemcpy(op->inv, hi, ni * 2, cudaMemcpyHostToDevice);
+    free(hf); free(hi);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { sb_operator_destroy(op); return fail(SB_ECUDA, "sb_operator_create: copy failed%s", ""); }
+    *out = op;
+    return SB_OK;
+}
+
+extern "C" void sb_operator_destroy(sb_operator *op) {
+    if (!op) return;
+    cudaFree(op->fwd);
+    cudaFree(op->inv);
+    delete op;
+}
+
+static AmpArgs base_args(const sb_operator *op, const int *sections, const int *nsec) {
+    AmpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.fwd = op->fwd; a.inv = op->inv; a.sections = sections; a.nsec = nsec;
+    a.L = op->L; a.n = op->n; a.Hp = op->Hp; a.NB = op->NB;
+    return a;
+}
+
+extern "C" int sb_amp_batch(const sb_operator *op, const double *y, const double *Pl, const double *beta0,
+                            const int *sections, const int *nsec, int B, int T, double *beta, int *iters, int *n_exec,
+                            unsigned *flags, double *tau2_trace, void *stream) {
+    if (!op || !y || !Pl || !beta || !iters || !n_exec || !flags || B < 0 || T < 0)
+        return fail(SB_EINVAL, "sb_amp_batch: null argument%s", "");
+    if ((sections == nullptr) != (nsec == nullptr)) return fail(SB_EINVAL, "sb_amp_batch: sections and nsec go together%s", "");
+    if (B == 0) return SB_OK;
+    AmpArgs a = base_args(op, sections, nsec);
+    a.y = y; a.Pl = Pl; a.beta0 = beta0; a.beta = beta; a.tau2_trace = tau2_trace;
+    a.iters = iters; a.n_exec = n_exec; a.flags = flags; a.T = T;
+    return dispatch(op, a, B, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int sb_Ab_batch(const sb_operator *op, const double *beta, const int *sections, const int *nsec, int B,
+                           double *out, void *stream) {
+    if (!op || !beta || !out || B < 0) return fail(SB_EINVAL, "sb_Ab_batch: null argument%s", "");
+    if ((sections == nullptr) != (nsec == nullptr)) return fail(SB_EINVAL, "sb_Ab_batch: sections and nsec go together%s", "");
+    if (B == 0) return SB_OK;
+    AmpArgs a = base_args(op, sections, nsec);
+    return dispatch(op, a, B, 1, beta, out, (cudaStream_t)stream);
+}
+
+extern "C" int sb_Az_batch(const sb_operator *op, const double *z, const int *sections, const int *nsec, int B,
+                           double *out, void *stream) {
+    if (!op || !z || !out || B < 0) return fail(SB_EINVAL, "sb_Az_batch: null argument%s", "");
+    if ((sections == nullptr) != (nsec == nullptr)) return fail(SB_EINVAL, "sb_Az_batch: sections and nsec go together%s", "");
+    if (B == 0) return SB_OK;
+    AmpArgs a = base_args(op, sections, nsec);
+    return dispatch(op, a, B, 2, z, out, (cudaStream_t)stream);
+}
+
+extern "C" int sb_onehot_apply_batch(const sb_operator *op, const int *idx, const double *Pl, const double *y,
+                                     double sign, int B, double *out, void *stream) {
+    if (!op || !idx || !Pl || !out || B < 0) return fail(SB_EINVAL, "sb_onehot_apply_batch: null argument%s", "");
+    if (B == 0) return SB_OK;
+    const int nt = 256;
+    dim3 grid((op->n + nt - 1) / nt, B);
+    const size_t smem = sizeof(int) * ((op->L + 1) & ~1) + sizeof(double) * op->L;
+    if (smem > 48 * 1024)
+        SB_CUDA(cudaFuncSetAttribute(onehot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    onehot_kernel<<<grid, nt, smem, (cudaStream_t)stream>>>(op->fwd, op->L, op->n, idx, Pl, y, sign, out);
+    SB_LAUNCHED();
+    return SB_OK;
+}

@@ -1,0 +1,91 @@
+// common.cuh -- shared helpers for libsparc_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/sparc_b200.h"
+
+namespace sb {
+
+extern thread_local char g_err[512];
+extern std::atomic<long> g_launches;
+
+inline int fail(int code, const char *fmt, const char *a = "", long b = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+#define SB_CUDA(call)                                                                           \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            snprintf(sb::g_err, sizeof(sb::g_err), "%s:%d %s: %s", __FILE__, __LINE__, #call,   \
+                     cudaGetErrorString(e__));                                                  \
+            return e__ == cudaErrorMemoryAllocation ? SB_ENOMEM : SB_ECUDA;                     \
+        }                                                                                       \
+    } while (0)
+
+#define SB_LAUNCHED()                                   \
+    do {                                                \
+        sb::g_launches.fetch_add(1);                    \
+        SB_CUDA(cudaGetLastError());                    \
+    } while (0)
+
+inline int ilog2(int v) {
+    int r = 0;
+    while ((1 << r) < v) r++;
+    return r;
+}
+
+// Deterministic CTA-wide sum: xor-shuffle tree inside each warp, then thread 0 adds the warp
+// partials in warp order.  `scratch` needs >= 33 doubles.  All threads get the result.
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = scratch[0];
+        for (int i = 1; i < nw; i++) s += scratch[i];
+        scratch[32] = s;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+__device__ __forceinline__ double block_max(double v, double *scratch) {
+    for (int d = 16; d; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = scratch[0];
+        for (int i = 1; i < nw; i++) s = fmax(s, scratch[i]);
+        scratch[32] = s;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+}  // namespace sb
+
+struct sb_operator {
+    int L, M, n, logM, w, H, Hp, NB;  // H = w/M blocks, Hp = padded to a multiple of 16, NB = Hp/16
+    uint16_t *fwd;                    // [L][n]   lo | sign<<15         (A beta gather)
+    uint16_t *inv;                    // [L][M][Hp] k or 0xFFFF, visit (bit-reversed hi) order (A^T z fold)
+};
+
+struct sb_graph {
+    int Nv, Nc, Nmsg, dcmax, dvmax;
+    int *voff;     // [Nv+1]  prefix sums of vdeg
+    int *vpos;     // [Nmsg]  internal message slot of each variable port
+    int *cbase;    // [Nc]    internal slot of port 0 of each check
+    int *cstride;  // [Nc]    slot stride between ports (= size of the check's degree class)
+    int *cdeg;     // [Nc]
+    int *ext2int;  // [Nmsg]  reference (check-major) message index -> internal slot
+};

@@ -1,0 +1,309 @@
+"""Device-side engine: thin torch wrappers over the C ABI (include/sparc_b200.h).
+
+torch is used for what it is good at here -- device memory, streams, torch.distributed -- and nothing
+else: every computation below is one call into libsparc_b200.so with raw device pointers.  All tensors
+are CUDA float64 / int32, row-major, codeword-major ([B, ...]).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+
+F64, I32 = torch.float64, torch.int32
+_RULES = {"sumprod2": _lib.SB_BP_SUMPROD2, "sumprod": _lib.SB_BP_SUMPROD, "minsum": _lib.SB_BP_MINSUM}
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise _lib.SparcB200Error("no CUDA device: libsparc_b200 has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError("%s must be a contiguous CUDA %s tensor" % (name, dtype))
+
+
+def transform_width(M, n):
+    """w of sparc_ldpc.py:54,110."""
+    return 2 ** int(np.ceil(np.log2(max(M + 1, n + 1))))
+
+
+def make_ordering(L, M, n, seed=0):
+    """Row-selection table of the block sub-sampled Hadamard design (sparc_ldpc.py:110-117): cumulative
+    in-place shuffles of arange(1, w) with RandomState(seed) -- host logic, shared by the whole batch."""
+    w = transform_width(M, n)
+    rng = np.random.RandomState(seed)
+    ordering = np.empty((L, n), dtype=np.uint32)
+    idxs = np.arange(1, w, dtype=np.uint32)
+    for ll in range(L):
+        rng.shuffle(idxs)
+        ordering[ll] = idxs[:n]
+    return ordering
+
+
+class AmpResult:
+    __slots__ = ("beta", "iters", "n_exec", "flags", "tau2")
+
+    def __init__(self, beta, iters, n_exec, flags, tau2):
+        self.beta, self.iters, self.n_exec, self.flags, self.tau2 = beta, iters, n_exec, flags, tau2
+
+
+class Operator:
+    """Device handle of the design operator for one (L, M, n, ordering)."""
+
+    def __init__(self, L, M, n, ordering=None, seed=0):
+        self.L, self.M, self.n = int(L), int(M), int(n)
+        self.logM = int(np.log2(M))
+        if ordering is None:
+            ordering = make_ordering(L, M, n, seed)
+        self.ordering = np.ascontiguousarray(ordering, dtype=np.uint32)
+        if self.ordering.shape != (self.L, self.n):
+            raise ValueError("ordering must have shape (L, n)")
+        _dev()
+        import ctypes as ct
+        h = ct.c_void_p()
+        check(_lib.lib().sb_operator_create(self.ordering.ctypes.data, self.L, self.M, self.n, ct.byref(h)),
+              "sb_operator_create")
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().sb_operator_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def _lists(self, sections, nsec, B):
+        if sections is None:
+            return None, None
+        _chk(sections, I32, "sections")
+        _chk(nsec, I32, "nsec")
+        if sections.shape != (B, self.L) or nsec.shape != (B,):
+            raise ValueError("sections must be [B, L] and nsec [B]")
+        return sections, nsec
+
+    def Ab(self, beta, sections=None, nsec=None):
+        """[B, L*M] (compact over the section list) -> A beta [B, n]   (sparc_ldpc.py:143-144)."""
+        _chk(beta, F64, "beta")
+        B = beta.shape[0]
+        if beta.shape[1] != self.L * self.M:
+            raise ValueError("beta rows must have L*M entries")
+        sections, nsec = self._lists(sections, nsec, B)
+        out = torch.empty((B, self.n), dtype=F64, device=beta.device)
+        check(_lib.lib().sb_Ab_batch(self._h, _p(beta), _p(sections), _p(nsec), B, _p(out), _stream()), "sb_Ab_batch")
+        return out
+
+    def Az(self, z, sections=None, nsec=None):
+        """[B, n] -> A^T z [B, L*M]   (sparc_ldpc.py:145-146); rows beyond nsec*M are zero."""
+        _chk(z, F64, "z")
+        B = z.shape[0]
+        sections, nsec = self._lists(sections, nsec, B)
+        out = torch.zeros((B, self.L * self.M), dtype=F64, device=z.device)
+        check(_lib.lib().sb_Az_batch(self._h, _p(z), _p(sections), _p(nsec), B, _p(out), _stream()), "sb_Az_batch")
+        return out
+
+    def onehot_apply(self, idx, Pl, y=None, sign=1.0):
+        """y + sign * A beta_onehot(idx) with beta_onehot[l*M+idx[l]] = sqrt(n Pl[l]); idx < 0 skips a section."""
+        _chk(idx, I32, "idx")
+        _chk(Pl, F64, "Pl")
+        _chk(y, F64, "y")
+        B = idx.shape[0]
+        out = torch.empty((B, self.n), dtype=F64, device=idx.device)
+        check(_lib.lib().sb_onehot_apply_batch(self._h, _p(idx), _p(Pl), _p(y), float(sign), B, _p(out), _stream()),
+              "sb_onehot_apply_batch")
+        return out
+
+    def amp(self, y, Pl, T, beta0=None, sections=None, nsec=None, trace=False):
+        """Batched AMP decode (sparc_ldpc.py:189-222).  Returns AmpResult."""
+        _chk(y, F64, "y")
+        _chk(Pl, F64, "Pl")
+        _chk(beta0, F64, "beta0")
+        B = y.shape[0]
+        if y.shape[1] != self.n or Pl.numel() != self.L:
+            raise ValueError("y must be [B, n] and Pl [L]")
+        sections, nsec = self._lists(sections, nsec, B)
+        dev = y.device
+        alloc = torch.empty if sections is None else torch.zeros
+        beta = alloc((B, self.L * self.M), dtype=F64, device=dev)
+        iters = torch.empty(B, dtype=I32, device=dev)
+        n_exec = torch.empty(B, dtype=I32, device=dev)
+        flags = torch.empty(B, dtype=I32, device=dev)
+        tau2 = torch.full((B, max(T, 1)), float("nan"), dtype=F64, device=dev) if trace else None
+        check(_lib.lib().sb_amp_batch(self._h, _p(y), _p(Pl), _p(beta0), _p(sections), _p(nsec), B, int(T), _p(beta),
+                                      _p(iters), _p(n_exec), _p(flags), _p(tau2), _stream()), "sb_amp_batch")
+        return AmpResult(beta, iters, n_exec, flags, tau2)
+
+
+_OP_CACHE = {}
+
+
+def get_operator(L, M, n, seed=0):
+    """Operators with a fixed seed are shared by every codeword (sparc_ldpc.py:140 default seed=0)."""
+    if seed is None:
+        return Operator(L, M, n, seed=None)
+    key = (L, M, n, seed, torch.cuda.current_device())
+    if key not in _OP_CACHE:
+        _OP_CACHE[key] = Operator(L, M, n, seed=seed)
+    return _OP_CACHE[key]
+
+
+class Graph:
+    """Device handle of a Tanner graph given by (vdeg, cdeg, intrlv) of ldpc.py:694-786."""
+
+    def __init__(self, vdeg, cdeg, intrlv):
+        import ctypes as ct
+        self.vdeg = np.ascontiguousarray(vdeg, dtype=np.int64)
+        self.cdeg = np.ascontiguousarray(cdeg, dtype=np.int64)
+        self.intrlv = np.ascontiguousarray(intrlv, dtype=np.int64)
+        self.Nv, self.Nc, self.Nmsg = len(self.vdeg), len(self.cdeg), len(self.intrlv)
+        _dev()
+        h = ct.c_void_p()
+        check(_lib.lib().sb_graph_create(self.vdeg.ctypes.data, self.cdeg.ctypes.data, self.intrlv.ctypes.data,
+                                         self.Nv, self.Nc, self.Nmsg, ct.byref(h)), "sb_graph_create")
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().sb_graph_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def bp(self, ch, dectype="sumprod2", corr_factor=0.7, max_it=_lib.SB_MAX_ITCOUNT):
+        _chk(ch, F64, "ch")
+        if dectype not in _RULES:
+            raise NameError("Decoder type unknonwn")
+        B = ch.shape[0]
+        if ch.shape[1] != self.Nv:
+            raise NameError("Channel inputs not consistent with variable degrees")
+        app = torch.empty_like(ch)
+        it = torch.empty(B, dtype=I32, device=ch.device)
+        check(_lib.lib().sb_bp_batch(self._h, _RULES[dectype], _p(ch), B, _p(app), _p(it), int(max_it),
+                                     float(corr_factor), _stream()), "sb_bp_batch")
+        return app, it
+
+
+# ---------------------------------------------------------------------------------------- handoff kernels
+def sp2bp_llr(beta, M, n, Pl, beta_first=0, first_sec=0, out_first=0, count=None, sections=None, nsec=None,
+              out=None, out_bits=None, want_p=False):
+    """LLRs (and optionally bit posteriors) of sections of beta [B, *]; see sb_sp2bp_llr_batch."""
+    _chk(beta, F64, "beta")
+    _chk(Pl, F64, "Pl")
+    B = beta.shape[0]
+    logM = int(np.log2(M))
+    Lstride = 0
+    if sections is not None:
+        _chk(sections, I32, "sections")
+        _chk(nsec, I32, "nsec")
+        Lstride = sections.shape[1]
+        count = 0
+    if out is None:
+        if out_bits is None:
+            out_bits = (out_first + count) * logM
+        out = torch.zeros((B, out_bits), dtype=F64, device=beta.device)
+    _chk(out, F64, "out")
+    p = torch.zeros_like(out) if want_p else None
+    check(_lib.lib().sb_sp2bp_llr_batch(_p(beta), beta.stride(0), int(beta_first), _p(sections), _p(nsec), int(Lstride),
+                                        int(first_sec), int(out_first), int(count), int(M), int(n), _p(Pl), B, _p(p),
+                                        _p(out), out.stride(0), _stream()), "sb_sp2bp_llr_batch")
+    return (out, p) if want_p else out
+
+
+def bp2sp_prior(app, ls, beta_prev, L, M, n, Pl, scale_by_power=True, from_prob=False):
+    """Next AMP initialisation / section posterior from LDPC a-posteriori LLRs (sparc_ldpc.py:685-696)."""
+    _chk(app, F64, "app")
+    _chk(beta_prev, F64, "beta_prev")
+    _chk(Pl, F64, "Pl")
+    B = app.shape[0] if app is not None else beta_prev.shape[0]
+    dev = app.device if app is not None else beta_prev.device
+    out = torch.empty((B, L * M), dtype=F64, device=dev)
+    check(_lib.lib().sb_bp2sp_prior_batch(_p(app), int(ls), _p(beta_prev), int(L), int(M), int(n), _p(Pl),
+                                          (1 if scale_by_power else 0) | (2 if from_prob else 0), B, _p(out),
+                                          _stream()), "sb_bp2sp_prior_batch")
+    return out
+
+
+def argmax_sections(beta, count, M, out=None):
+    _chk(beta, F64, "beta")
+    B = beta.shape[0]
+    if out is None:
+        out = torch.empty((B, count), dtype=I32, device=beta.device)
+    check(_lib.lib().sb_argmax_batch(_p(beta), beta.stride(0), int(count), int(M), B, _p(out), out.stride(0), _stream()),
+          "sb_argmax_batch")
+    return out
+
+
+def llr2idx(llr, count, M, out=None):
+    """Hard decisions (llr < 0) packed MSB first into section indices; `out` may be a column slice view."""
+    _chk_strided = llr.is_cuda and llr.dtype == F64 and llr.stride(1) == 1
+    if not _chk_strided:
+        raise ValueError("llr must be a CUDA float64 tensor with unit inner stride")
+    B = llr.shape[0]
+    if out is None:
+        out = torch.empty((B, count), dtype=I32, device=llr.device)
+    check(_lib.lib().sb_llr2idx_batch(llr.data_ptr(), llr.stride(0), int(count), int(M), B, out.data_ptr(),
+                                      out.stride(0), _stream()), "sb_llr2idx_batch")
+    return out
+
+
+def count_errors(a, t):
+    """Bit errors per codeword: sum_i popcount(a[b,i] ^ t[b,i]) (sparc_ldpc.py:650)."""
+    _chk(a, I32, "a")
+    _chk(t, I32, "t")
+    B, count = a.shape
+    out = torch.empty(B, dtype=I32, device=a.device)
+    check(_lib.lib().sb_count_errors_batch(_p(a), _p(t), int(count), B, _p(out), _stream()), "sb_count_errors_batch")
+    return out
+
+
+def onehot_beta(idx, Pl, n, L, M):
+    """Hard-decided beta (sparc_ldpc.py:840-843): sqrt(n Pl[l]) at idx[b, l], zero elsewhere."""
+    _chk(idx, I32, "idx")
+    _chk(Pl, F64, "Pl")
+    B = idx.shape[0]
+    beta = torch.empty((B, L * M), dtype=F64, device=idx.device)
+    check(_lib.lib().sb_onehot_beta_batch(_p(idx), _p(Pl), int(n), int(L), int(M), B, _p(beta), _stream()),
+          "sb_onehot_beta_batch")
+    return beta
+
+
+def threshold_peel(post, L, M, ls, threshold):
+    """amp_exit.py:85-106 -> (hard_idx [B, L], act [B, L], nact [B])."""
+    _chk(post, F64, "post")
+    B = post.shape[0]
+    dev = post.device
+    hard = torch.empty((B, L), dtype=I32, device=dev)
+    act = torch.empty((B, L), dtype=I32, device=dev)
+    nact = torch.empty(B, dtype=I32, device=dev)
+    check(_lib.lib().sb_threshold_peel_batch(_p(post), int(L), int(M), int(ls), float(threshold), B, _p(hard), _p(act),
+                                             _p(nact), _stream()), "sb_threshold_peel_batch")
+    return hard, act, nact
+
+
+def exit_hist(E, X, edges):
+    """counts [B, 2, nbins] (row 0: X == +1, row 1: X == -1) with numpy.histogram semantics."""
+    _chk(E, F64, "E")
+    _chk(X, I32, "X")
+    _chk(edges, F64, "edges")
+    B, length = E.shape
+    nb = edges.numel() - 1
+    counts = torch.empty((B, 2, nb), dtype=torch.int64, device=E.device)
+    check(_lib.lib().sb_exit_hist_batch(_p(E), _p(X), int(length), _p(edges), int(edges.numel()), B, _p(counts),
+                                        _stream()), "sb_exit_hist_batch")
+    return counts

@@ -1,0 +1,449 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors of the
+unmodified reference.  Integer / index / add-only quantities are compared bit for bit; quantities that pass
+through exp/log are compared to 1e-9 relative (the north-star tolerance is 1e-5 relative on beta and tau^2
+per iteration -- asserted separately with the measured margin printed)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import FLOW_CASES, flat_result, golden
+
+pytestmark = pytest.mark.gpu
+
+NORTH_STAR_RTOL = 1e-5   # BASELINE.json: beta / tau^2 per iteration within 1e-5 relative
+TIGHT = 1e-9             # what fp64 kernels in the reference's add order actually achieve (with margin)
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def relinf(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def S():
+    from sparc_ldpc_b200 import sparc_ldpc
+    return sparc_ldpc
+
+
+@pytest.fixture(scope="module")
+def Eng():
+    from sparc_ldpc_b200 import engine
+    return engine
+
+
+# ------------------------------------------------------------------------------------------- operators
+@pytest.mark.parametrize("tag", ["a", "b", "c1", "c"])
+def test_operators_bit_exact(Eng, tag):
+    g = golden("ops")
+    L, M, n = (int(v) for v in g[tag + "_shape"])
+    op = Eng.Operator(L, M, n, seed=0)
+    assert np.array_equal(op.ordering, g[tag + "_ordering"])
+    Ab = op.Ab(cu(g[tag + "_b"].reshape(1, -1))).cpu().numpy().reshape(-1)
+    Az = op.Az(cu(g[tag + "_z"].reshape(1, -1))).cpu().numpy().reshape(-1)
+    assert np.array_equal(Ab, g[tag + "_Ab"])
+    assert np.array_equal(Az, g[tag + "_Az"])
+    # sparc_transforms_shorter on a fancy-indexed row set, via section lists on the same tables
+    sub = g[tag + "_sub"]
+    sec = np.zeros((1, L), dtype=np.int32)
+    sec[0, :len(sub)] = sub
+    nsec = cu(np.array([len(sub)], dtype=np.int32))
+    b = np.zeros((1, L * M))
+    b[0, :len(sub) * M] = g[tag + "_b"][:len(sub) * M]
+    assert np.array_equal(op.Ab(cu(b), cu(sec), nsec).cpu().numpy().reshape(-1), g[tag + "_Ab_sub"])
+    assert np.array_equal(op.Az(cu(g[tag + "_z"].reshape(1, -1)), cu(sec), nsec).cpu().numpy().reshape(-1)[:len(sub) * M],
+                          g[tag + "_Az_sub"])
+
+
+def test_facade_closures(S):
+    g = golden("ops")
+    L, M, n = (int(v) for v in g["b_shape"])
+    Ab, Az, ordering = S.sparc_transforms(L, M, n)
+    assert Ab(g["b_b"]).shape == (n, 1) and Az(g["b_z"].reshape(-1, 1)).shape == (L * M, 1)
+    assert np.array_equal(Ab(g["b_b"].reshape(-1, 1)).reshape(-1), g["b_Ab"])
+    sub = g["b_sub"]
+    Ab2, Az2 = S.sparc_transforms_shorter(len(sub), M, n, ordering[sub, :])
+    assert np.array_equal(Ab2(g["b_b"][:len(sub) * M]).reshape(-1), g["b_Ab_sub"])
+    assert np.array_equal(Az2(g["b_z"]).reshape(-1), g["b_Az_sub"])
+
+
+def test_onehot_encoder_equals_operator(Eng, oracle):
+    L, M, n = 64, 8, 192
+    op = Eng.get_operator(L, M, n, 0)
+    rs = np.random.RandomState(2)
+    idx = rs.randint(0, M, (3, L)).astype(np.int32)
+    Pl = 4.0 / L * np.ones(L)
+    Abo, _, _ = oracle.sparc_transforms(L, M, n)
+    x = op.onehot_apply(cu(idx), cu(Pl)).cpu().numpy()
+    y = rs.randn(3, n)
+    idx2 = idx.copy()
+    idx2[:, ::3] = -1
+    xm = op.onehot_apply(cu(idx2), cu(Pl), cu(y), sign=-1.0).cpu().numpy()
+    for b in range(3):
+        b0 = np.zeros(L * M)
+        b0[np.arange(L) * M + idx[b]] = np.sqrt(n * Pl)
+        assert np.array_equal(x[b], Abo(b0).reshape(-1))
+        b1 = b0.reshape(L, M).copy()
+        b1[::3] = 0
+        assert np.array_equal(xm[b], (y[b].reshape(-1, 1) - Abo(b1.reshape(-1))).reshape(-1))
+
+
+def test_operator_linearity_full_size(Eng):
+    """Size-independent property at the headline shape: A(a x + b y) == a A x + b A y up to fp64 rounding."""
+    L, M, n = 512, 512, 4608
+    op = Eng.get_operator(L, M, n, 0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn((2, L * M), dtype=torch.float64, device="cuda", generator=g)
+    mix = (0.75 * x[0] - 1.25 * x[1]).reshape(1, -1)
+    Ax = op.Ab(x)
+    Am = op.Ab(mix)
+    assert relinf((0.75 * Ax[0] - 1.25 * Ax[1]).cpu().numpy(), Am[0].cpu().numpy()) < 1e-12
+    # <A^T z, x> == <z, A x>
+    z = torch.randn((1, n), dtype=torch.float64, device="cuda", generator=g)
+    lhs = float((op.Az(z)[0] * x[0]).sum())
+    rhs = float((z[0] * Ax[0]).sum())
+    assert abs(lhs - rhs) / abs(rhs) < 1e-11
+
+
+# ------------------------------------------------------------------------------------------- AMP
+def _amp_trace(op, y, Pl, T, beta0=None):
+    """beta after each iteration by re-running with T = 1..; returns (betas, last result)."""
+    yd, Pld = cu(y.reshape(1, -1)), cu(Pl)
+    b0 = None if beta0 is None else cu(beta0.reshape(1, -1))
+    full = op.amp(yd, Pld, T, beta0=b0, trace=True)
+    nex = int(full.n_exec[0])
+    betas = [op.amp(yd, Pld, t, beta0=b0).beta.cpu().numpy().reshape(-1) for t in range(1, nex + 1)]
+    return betas, full
+
+
+@pytest.mark.parametrize("k", [0, 1, "w"])
+def test_amp_trace_c1(Eng, k):
+    g = golden("amp_small")
+    L, M, P, T, n = 128, 4, 2.0, 64, 256
+    Pl = P / L * np.ones(L)
+    op = Eng.get_operator(L, M, n, 0)
+    p = "c1_w_" if k == "w" else "c1_%d_" % k
+    y = g["c1_0_y"] if k == "w" else g[p + "y"]
+    betas, full = _amp_trace(op, y, Pl, T, g["c1_w_init"] if k == "w" else None)
+    assert int(full.iters[0]) == int(g[p + "t"])
+    tau2 = full.tau2.cpu().numpy().reshape(-1)[:len(betas)]
+    err_t = relinf(tau2, g[p + "tau2"][:len(betas)])
+    err_b = max(relinf(b, r) for b, r in zip(betas, g[p + "beta_trace"]))
+    print("C1 %s: max rel err tau2 %.2e, beta %.2e over %d iterations" % (k, err_t, err_b, len(betas)))
+    assert len(betas) == len(g[p + "beta_trace"])
+    assert err_t < NORTH_STAR_RTOL and err_b < NORTH_STAR_RTOL
+    assert err_t < TIGHT and err_b < TIGHT
+    assert relinf(full.beta.cpu().numpy().reshape(-1), g[p + "beta"]) < TIGHT
+
+
+def test_amp_power_allocation(Eng):
+    g = golden("amp_small")
+    L, M, T = 32, 64, 64
+    n = L * 6
+    op = Eng.get_operator(L, M, n, 0)
+    betas, full = _amp_trace(op, g["pa_y"], g["pa_Pl"], T)
+    assert int(full.iters[0]) == int(g["pa_t"])
+    err_b = max(relinf(b, r) for b, r in zip(betas, g["pa_beta_trace"]))
+    err_t = relinf(full.tau2.cpu().numpy().reshape(-1)[:len(betas)], g["pa_tau2"][:len(betas)])
+    print("PA: max rel err tau2 %.2e beta %.2e" % (err_t, err_b))
+    assert err_b < TIGHT and err_t < TIGHT
+
+
+@pytest.mark.parametrize("k", [0, 1])
+def test_amp_c3_shape(Eng, S, k):
+    """L = M = 512, n = 4608: tau^2 per iteration, per-section argmax / max per iteration, early-stop index."""
+    g = golden("amp_c3")
+    L, M, n, T = 512, 512, 4608, 64
+    Pl = 4.0 / L * np.ones(L)
+    op = Eng.get_operator(L, M, n, 0)
+    p = "c3_%d_" % k
+    yd, Pld = cu(g[p + "y"].reshape(1, -1)), cu(Pl)
+    full = op.amp(yd, Pld, T, trace=True)
+    nex = int(full.n_exec[0])
+    assert int(full.iters[0]) == int(g[p + "t"]), (int(full.iters[0]), int(g[p + "t"]))
+    assert nex == len(g[p + "tau2"]) == len(g[p + "sumsq_trace"])
+    tau2 = full.tau2.cpu().numpy().reshape(-1)[:nex]
+    err_t = relinf(tau2, g[p + "tau2"][:nex])
+    worst = 0.0
+    for t in (1, 2, 5, 10, nex):
+        if t > nex:
+            continue
+        r = op.amp(yd, Pld, t)
+        b = r.beta.cpu().numpy().reshape(L, M)
+        assert np.array_equal(b.argmax(axis=1), g[p + "argmax_trace"][t - 1])
+        worst = max(worst, relinf(b.max(axis=1), g[p + "max_trace"][t - 1]),
+                    abs(np.sum(b ** 2) - g[p + "sumsq_trace"][t - 1]) / g[p + "sumsq_trace"][t - 1])
+    post = full.beta.cpu().numpy().reshape(-1) / np.sqrt(n * np.repeat(Pl, M))
+    bitwise = S.sp2bp(post, L, M)
+    err_p = float(np.max(np.abs(bitwise - g[p + "bitwise"])))
+    print("C3 %d: %d iterations, rel err tau2 %.2e, section max %.2e, |d bitwise| %.2e" % (k, nex, err_t, worst, err_p))
+    assert err_t < NORTH_STAR_RTOL and worst < NORTH_STAR_RTOL
+    assert err_t < 1e-8 and worst < 1e-8 and err_p < 1e-8
+
+
+def test_amp_batch_consistency_and_edge_cases(Eng):
+    """A batch decodes each codeword exactly as a batch of one; T = 0 and empty section lists are no-ops."""
+    g = golden("amp_small")
+    L, M, n = 128, 4, 256
+    Pl = cu(2.0 / L * np.ones(L))
+    op = Eng.get_operator(L, M, n, 0)
+    ys = cu(np.stack([g["c1_0_y"], g["c1_1_y"], g["c1_0_y"]]))
+    r = op.amp(ys, Pl, 64)
+    r0 = op.amp(ys[:1].contiguous(), Pl, 64)
+    assert torch.equal(r.beta[0], r0.beta[0]) and torch.equal(r.beta[0], r.beta[2])
+    assert r.iters.tolist()[0] == int(g["c1_0_t"])
+    z0 = op.amp(ys, Pl, 0)
+    assert float(z0.beta.abs().max()) == 0.0 and z0.n_exec.tolist() == [0, 0, 0]
+    sec = torch.zeros((3, L), dtype=torch.int32, device="cuda")
+    nsec = torch.tensor([0, L, 0], dtype=torch.int32, device="cuda")
+    sec[1] = torch.arange(L, dtype=torch.int32)
+    e = op.amp(ys, Pl, 64, sections=sec, nsec=nsec)
+    assert e.n_exec.tolist()[0] == 0 and e.n_exec.tolist()[2] == 0
+    assert torch.equal(e.beta[1], r.beta[1])
+
+
+# ------------------------------------------------------------------------------------------- handoff
+def test_handoff_known_answers(S):
+    g = golden("handoff")
+    np.testing.assert_allclose(S.sp2bp(g["kat1_in"], 2, 4), [0.1, 0.15, 0.95, 0.9], rtol=1e-15)       # removed.py:40-49
+    np.testing.assert_allclose(S.sp2bp(g["kat2_in"], 2, 4), [0.5, 0.7, 0, 0.4], rtol=1e-15)           # removed.py:203-204
+    assert np.array_equal(S.sp2bp(g["kat1_in"], 2, 4), g["kat1_bp"])
+    assert np.array_equal(S.bp2sp(g["kat1_bp"], 2, 4), g["kat1_back"])
+
+
+@pytest.mark.parametrize("tag,L,M", [("m4", 16, 4), ("m32", 8, 32), ("m512", 3, 512)])
+def test_handoff_maps(S, Eng, tag, L, M):
+    g = golden("handoff")
+    logm = int(np.log2(M))
+    assert np.array_equal(S.sp2bp(g[tag + "_sec"], L, M), g[tag + "_bp"])          # sequential adds: bit exact
+    ones = cu(np.ones(L))
+    llr = Eng.sp2bp_llr(cu(g[tag + "_sec"].reshape(1, -1)), M, 1, ones, count=L).cpu().numpy().reshape(-1)
+    ref = g[tag + "_llr"]
+    big = np.abs(ref) > 1e300
+    assert np.array_equal(np.abs(llr) > 1e300, big) and np.array_equal(llr[big], ref[big])   # +-DBL_MAX class
+    assert np.array_equal(llr == 0, ref == 0)                                                # NaN -> 0 class
+    np.testing.assert_allclose(llr[~big], ref[~big], rtol=1e-13, atol=1e-300)
+    assert np.array_equal(S.bp2sp(g[tag + "_bw"], L, M), g[tag + "_sp"])           # products + numpy-order sum
+    sp = Eng.bp2sp_prior(cu(g[tag + "_app"].reshape(1, -1)), L, None, L, M, 1, ones, False).cpu().numpy().reshape(-1)
+    np.testing.assert_allclose(sp, g[tag + "_sp"], rtol=1e-13, atol=1e-300)
+    idx = Eng.llr2idx(cu((0.5 - g[tag + "_bits"]).reshape(1, -1).astype(np.float64)), L, M).cpu().numpy().reshape(-1)
+    assert np.array_equal(idx, g[tag + "_idx"])
+    assert S.ber_from_LLRs(M, g[tag + "_llr"], g[tag + "_idx"].tolist(), L * logm) == float(g[tag + "_ber"])
+    am = Eng.argmax_sections(cu(g[tag + "_sec"].reshape(1, -1)), L, M).cpu().numpy().reshape(-1)
+    assert np.array_equal(am, g[tag + "_sec"].reshape(L, M).argmax(axis=1))
+
+
+def test_argmax_first_maximum_and_peel(Eng):
+    b = np.zeros((2, 3 * 8))
+    b[0, 2] = b[0, 5] = 1.0          # tie: first wins
+    b[0, 8 + 7] = 0.3
+    b[1, 16 + 1] = 0.9
+    b[1, 16 + 6] = 0.8               # two entries above threshold -> not peeled
+    am = Eng.argmax_sections(cu(b), 3, 8).cpu().numpy()
+    assert am[0].tolist() == [2, 7, 0] and am[1].tolist() == [0, 0, 1]
+    hard, act, nact = Eng.threshold_peel(cu(b), 3, 8, 2, 0.6)
+    assert hard.cpu().numpy().tolist() == [[-1, -1, -1], [-1, -1, -1]]
+    hard, act, nact = Eng.threshold_peel(cu(b), 3, 8, 3, 0.6)
+    assert hard.cpu().numpy().tolist() == [[-1, -1, -1], [-1, -1, -1]] and nact.tolist() == [3, 3]
+    b[0, 5] = 0.0
+    hard, act, nact = Eng.threshold_peel(cu(b), 3, 8, 3, 0.6)
+    assert hard.cpu().numpy().tolist()[0] == [2, -1, -1] and act.cpu().numpy()[0, :2].tolist() == [1, 2] and nact.tolist() == [2, 3]
+    hard, act, nact = Eng.threshold_peel(cu(b), 3, 8, 2, 0.6)   # section 0 unprotected: never peeled
+    assert hard.cpu().numpy().tolist()[0] == [-1, -1, -1]
+
+
+# ------------------------------------------------------------------------------------------- BP
+def test_bp_against_reference_golden():
+    from sparc_ldpc_b200 import ldpc
+    g = golden("ldpc")
+    for i in range(int(g["n_codes"])):
+        p = "k%d_" % i
+        std, rate, z, pt = g[p + "name"]
+        c = ldpc.code(str(std), str(rate), int(z), str(pt))
+        app, it = c.decode_batch(cu(g[p + "ch"]))
+        app, it = app.cpu().numpy(), it.cpu().numpy()
+        assert it.tolist() == g[p + "it"].tolist(), (std, rate, z, it, g[p + "it"])
+        for j in range(3):
+            assert np.array_equal(app[j] < 0, g[p + "app"][j] < 0)
+            if it[j] < 200:   # converged: compare values; non-convergent 200-iteration orbits are chaotic
+                np.testing.assert_allclose(app[j], g[p + "app"][j], rtol=1e-8, atol=1e-8)
+        # the reference's own FFI symbol (host pointers) gives the same answer as the batch entry point
+        a1, it1 = c.decode(g[p + "ch"][1])
+        assert it1 == it[1] and np.array_equal(a1, app[1])
+        if p + "app_sumprod" in g:
+            a, t = c.decode(g[p + "ch"][1], "sumprod")
+            assert t == int(g[p + "it_sumprod"])
+            np.testing.assert_allclose(a, g[p + "app_sumprod"], rtol=1e-8, atol=1e-8)
+        if p + "app_minsum" in g:
+            a, t = c.decode(g[p + "ch"][1], "minsum", 0.7)
+            assert t == int(g[p + "it_minsum"])
+            np.testing.assert_allclose(a, g[p + "app_minsum"], rtol=1e-12, atol=1e-12)
+    out = np.array([c.Lxor(a, b) for a, b in g["lxor_in"]])
+    np.testing.assert_allclose(out, g["lxor_out"], rtol=1e-14, equal_nan=True)
+    out = np.array([c.Lxor(a, b, 0) for a, b in g["lxor_in"]])
+    np.testing.assert_allclose(out, g["lxor_out_nocorr"], rtol=1e-15, equal_nan=True)
+    tot, ext = c.Lxfb(g["lxfb_in"])
+    np.testing.assert_allclose(tot, g["lxfb_tot"], rtol=1e-13)
+    np.testing.assert_allclose(ext, g["lxfb_ext"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("std,rate,z,pt", [("802.16", "1/2", 27, "A"), ("802.16", "2/3", 27, "B"), ("802.16", "3/4", 54, "A"),
+                                           ("802.16", "5/6", 81, "A"), ("802.11n", "1/2", 54, "A"), ("802.11n", "5/6", 81, "A"),
+                                           ("802.16", "5/6", 192, "A")])
+def test_reference_pytest_property_on_gpu(std, rate, z, pt):
+    """ldpc/py/test_ldpc.py:58-65 through our FFI: a noiseless word decodes in 0 iterations to itself."""
+    from sparc_ldpc_b200 import ldpc
+    c = ldpc.code(std, rate, z, pt)
+    rs = np.random.RandomState(0)
+    U = rs.randint(0, 2, (8, c.K))
+    X = c.encode_batch(U)
+    app, it = c.decode(np.array(10 * (.5 - X[0]), dtype=float))
+    assert it == 0 and np.array_equal((app < 0).astype(int), X[0])
+    app, it = c.decode_batch(cu(10 * (.5 - X.astype(np.float64))))
+    assert it.tolist() == [0] * 8 and np.array_equal((app < 0).cpu().numpy().astype(int), X)
+
+
+def test_bp_matches_oracle_on_fresh_noise(oracle):
+    from sparc_ldpc_b200 import ldpc
+    c = ldpc.code("802.16", "5/6", 48)
+    co = oracle.Code("802.16", "5/6", 48)
+    rs = np.random.RandomState(9)
+    X = c.encode_batch(rs.randint(0, 2, (16, c.K)))
+    s = 0.58
+    ch = 2 / s ** 2 * (1 - 2.0 * X + s * rs.randn(*X.shape))
+    app, it = c.decode_batch(cu(ch))
+    app, it = app.cpu().numpy(), it.cpu().numpy()
+    for b in range(16):
+        ao, io = co.decode(ch[b])
+        assert io == it[b]
+        assert np.array_equal(ao < 0, app[b] < 0)
+        if io < 200:
+            np.testing.assert_allclose(app[b], ao, rtol=1e-8, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------- link simulations
+@pytest.mark.parametrize("case", FLOW_CASES, ids=[c[0] for c in FLOW_CASES])
+def test_link_sims_against_reference(S, case):
+    """Same seeds, same draw order (legacy global numpy stream) -> identical BER lists as the reference."""
+    tag, fn, spk, lpk, kw, reps = case
+    g = golden("flows_small")
+    np.random.seed(int(g[tag + "_seed"]))
+    sp = S.SPARCParams(**spk)
+    lp = None if lpk is None else S.LDPCParams(*lpk)
+    rows = []
+    for _ in range(reps):
+        if fn == "amp_ldpc_sim":
+            res = S.amp_ldpc_sim(sp, lp)
+        elif fn == "soft_amp_ldpc_sim":
+            res = S.soft_amp_ldpc_sim(sp, lp, kw["soft_iter"])
+        elif fn == "hardinitbeta_amp_ldpc_sim":
+            res = S.hardinitbeta_amp_ldpc_sim(sp, lp)
+        else:
+            res = S.soft_amp_ldpc_hardinit(sp, lp, kw["soft_iter"], kw["threshold"])
+        rows.append(flat_result(res))
+    np.testing.assert_array_equal(np.array(rows), g[tag + "_res"])
+
+
+def test_batch_equals_sequential(S):
+    """B codewords in one pass == B single-codeword calls on the same RNG stream."""
+    sp = S.SPARCParams(L=64, M=8, sigma=0.8, p=4, r=1, t=64)
+    lp = S.LDPCParams("802.16", "5/6", 8)
+    rng = np.random.RandomState(5)
+    ba, bl, R = S.soft_amp_ldpc_sim_batch(sp, lp, 2, B=6, rng=rng)
+    np.random.seed(5)
+    for b in range(6):
+        a1, l1, R1 = S.soft_amp_ldpc_sim(sp, lp, 2)
+        assert a1 == ba[b].tolist() and l1 == bl[b].tolist() and R1 == R
+
+
+@pytest.mark.parametrize("tag", ["soft", "hard", "thr"])
+def test_c3_flows_against_reference(S, tag):
+    """One full-size codeword per flow: L = M = 512, 802.16 rate 5/6 z = 192 (BASELINE configs[2])."""
+    g = golden("flows_c3")
+    np.random.seed(int(g[tag + "_seed"]))
+    sp = S.SPARCParams(L=512, M=512, sigma=float(g[tag + "_sigma"]), p=4, r=1, t=64)
+    lp = S.LDPCParams("802.16", "5/6", 192)
+    if tag == "soft":
+        res = S.soft_amp_ldpc_sim(sp, lp, 2)
+    elif tag == "hard":
+        res = S.hardinitbeta_amp_ldpc_sim(sp, lp)
+    else:
+        res = S.soft_amp_ldpc_hardinit(sp, lp, 2, 0.6)
+    got, ref = flat_result(res), g[tag + "_res"]
+    print(tag, got, ref)
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_c3_soft_stage_internals(S, Eng):
+    """Per-stage internals of the full-size soft flow against the captured reference calls."""
+    from sparc_ldpc_b200 import decoder as D
+    g = golden("flows_c3")
+    sp = S.SPARCParams(L=512, M=512, sigma=float(g["soft_sigma"]), p=4, r=1, t=64)
+    su = D.make_setup(sp, S.LDPCParams("802.16", "5/6", 192))
+    y = cu(g["soft_y"].reshape(1, -1))
+    st = D.soft(su, y, 2)
+    for j in range(3):
+        assert np.array_equal(st.amp_idx[j].cpu().numpy().reshape(-1), g["soft_amp%d_argmax" % j])
+    assert [int(t[0]) for t in st.bp_it] == [int(g["soft_dec0_it"]), int(g["soft_dec1_it"])]
+    llr = Eng.sp2bp_llr(su.op.amp(y, su.Pl_dev, 64).beta, 512, su.n, su.Pl_dev, count=512).cpu().numpy().reshape(-1)
+    ref = g["soft_dec0_ch"]
+    sat = (np.abs(ref) > 1e300) | (ref == 0)
+    print("saturated LLRs in the reference: %d of %d" % (sat.sum(), ref.size))
+    assert np.array_equal(np.sign(llr[~sat]), np.sign(ref[~sat]))
+    np.testing.assert_allclose(llr[~sat], ref[~sat], rtol=1e-6, atol=1e-9)
+
+
+def test_headline_roundtrip_property(S):
+    """encode -> AWGN at high SNR -> soft decode: zero errors at every stage, full size, batch of 4."""
+    sp = S.SPARCParams(L=512, M=512, sigma=0.6, p=4, r=1, t=64)
+    ba, bl, R = S.soft_amp_ldpc_sim_batch(sp, S.LDPCParams("802.16", "5/6", 192), 2, B=4, rng=np.random.RandomState(1))
+    assert ba.shape == (4, 3) and bl.shape == (4, 2) and not ba.any() and not bl.any()
+    assert abs(R - 5 / 6) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------- EXIT chart
+def test_exit_chain_against_reference():
+    from sparc_ldpc_b200 import amp_exit as AE, sparc_ldpc as S2
+    g = golden("exit")
+    np.random.seed(77)
+    sp = S2.SPARCParams(L=64, M=8, sigma=None, p=4, r=1, t=64)
+    for k, (I_a, snr, thr) in enumerate(g["meta"]):
+        X = AE.gen_bits(64 * 3)
+        assert np.array_equal(X, g["X"][k])
+        Eo = AE.calc_E(X, I_a, snr, sp, threshold=thr)
+        ref = g["E"][k]
+        sat = np.abs(ref) >= 55
+        assert np.array_equal(np.abs(Eo) >= 55, sat)
+        np.testing.assert_allclose(Eo, ref, rtol=1e-7, atol=1e-7)
+        h = AE.hist_E(X, Eo, bin_number=60, max_bin=60, min_bin=-60)
+        np.testing.assert_allclose(AE.calc_I_e(h[0], h[1], h[6]), g["I_e"][k], rtol=1e-9)
+        if I_a == 0.5:
+            np.testing.assert_allclose(h[0], g["pe_pos"], rtol=1e-12)
+            np.testing.assert_allclose(h[1], g["pe_neg"], rtol=1e-12)
+            np.testing.assert_allclose(np.array(h[2:]), g["stats"], rtol=1e-9)
+    np.random.seed(78)
+    sp = S2.SPARCParams(L=256, M=32, sigma=None, p=4, r=1, t=64)
+    X = AE.gen_bits(256 * 5)
+    assert np.array_equal(X, g["c4_X"])
+    Eo = AE.calc_E(X, 0.66, 11.0, sp, threshold=0.7)
+    np.testing.assert_allclose(Eo, g["c4_E"], rtol=1e-7, atol=1e-7)
+    h = AE.hist_E(X, Eo, bin_number=350, max_bin=60, min_bin=-60)
+    np.testing.assert_allclose(AE.calc_I_e(h[0], h[1], h[6]), g["c4_I_e"], rtol=1e-9)
+
+
+def test_exit_histogram_semantics(Eng):
+    rs = np.random.RandomState(4)
+    Ev = np.clip(rs.randn(2, 500) * 30, -55, 55)
+    Ev[0, :4] = [-60.0, 60.0, 0.0, 59.999]
+    X = (rs.randint(0, 2, (2, 500)) * -2 + 1).astype(np.int32)
+    edges = np.linspace(-60, 60, 50)
+    cnt = Eng.exit_hist(cu(Ev), cu(X), cu(edges)).cpu().numpy()
+    for b in range(2):
+        for w, s in ((0, 1), (1, -1)):
+            ref, _ = np.histogram(Ev[b][X[b] == s], bins=edges)
+            assert np.array_equal(cnt[b, w], ref)
