@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Headline benchmark: decoded codewords/s (and info Mbit/s) of the SPARC-AMP + outer-LDPC soft-exchange
+decoder at L = M = 512, R = 1, P = 4, IEEE 802.16 rate-5/6 outer code (z = 192), 2 AMP<->BP iterations
+(BASELINE.json configs[2], the configuration `metric` is quoted on; it fits one GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+A "step" is one pass of the whole soft flow (AMP -> LLR -> BP -> prior -> AMP -> ... , 3 AMP decodes and
+2 BP decodes per codeword, sparc_ldpc.py:636-706) over one batch of B synthetic codewords per GPU.  `value`
+is measured with the received vectors y already resident in HBM; `e2e` runs the same step from pinned host
+buffers through the public API with the H2D copy of y and the D2H read of the decisions / error counts
+inside the timed region.  One process per GPU; codewords are independent, so ranks shard them (weak scaling)
+and the only collective is the NCCL all-reduce of the error counters.
+
+`--impl reference` times the reference's CPU algorithm (oracle port: numpy + C w-point FHT + the reference's
+own c_ldpc.c when oracle/_ref was built) on all host cores, one codeword per worker per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# workload (BASELINE.json configs[2]); Eb/N0 in the reference's 20 log10 convention, inside the waterfall
+# (ldpc/EbN0_dBVsBER_waterfallsoft_rep200_LM512p4r1rldpc5_6.csv row 7.667 dB)
+L, M, P, R_SPARC, T, SOFT_ITER = 512, 512, 4.0, 1, 64, 2
+STD, RATE, Z = "802.16", "5/6", 192
+EBN0_DB = 7.667
+R_TOTAL = 5.0 / 6.0
+N = int(L * np.log2(M) / R_SPARC)
+INFO_BITS = int(L * np.log2(M)) - (24 * Z - 20 * Z)      # L logM - (N_ldpc - K_ldpc) = 3840
+SIGMA = float(np.sqrt(P / ((10 ** (EBN0_DB / 20)) * 2 * R_TOTAL)))   # sparc_ldpc.py:1184,1199-1200
+WORKLOAD = "soft AMP<->LDPC exchange x2, L=M=512 R=1 P=4, 802.16 5/6 z=192, Eb/N0(ref dB)=%.3f" % EBN0_DB
+METRIC = "decoded codewords/sec at L=M=512 R=1 P=4 +LDPC5/6 (soft exchange, 2 AMP<->BP iterations)"
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_one(seed):
+    import warnings
+    warnings.simplefilter("ignore")
+    from oracle import oracle as orc
+    rng = np.random.RandomState(seed)
+    sp = orc.SPARCParams(L=L, M=M, sigma=SIGMA, p=P, r=R_SPARC, t=T)
+    t0 = time.perf_counter()
+    res = orc.soft_amp_ldpc_sim(sp, orc.LDPCParams(STD, RATE, Z), SOFT_ITER, rng=rng)
+    return time.perf_counter() - t0, res[0], res[1]
+
+
+def _ensure_oracle():
+    if not os.path.isfile(os.path.join(ROOT, "oracle", "_build", "liboracle.so")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_build/liboracle.so"],
+                              stdout=subprocess.DEVNULL)
+
+
+def cpu_run(steps, warmup, cores=None):
+    """steps x (one soft-flow codeword per worker, all workers in parallel).  Returns cw/s and details."""
+    import multiprocessing as mp
+    _ensure_oracle()
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for w in range(warmup):
+            pool.map(_cpu_one, [10_000 + w * cores + i for i in range(cores)])
+        t0 = time.perf_counter()
+        per = []
+        for s in range(steps):
+            per += pool.map(_cpu_one, [20_000 + s * cores + i for i in range(cores)])
+        wall = time.perf_counter() - t0
+    single = float(np.mean([p[0] for p in per]))
+    return dict(value=cores * steps / wall, wall=wall, cores=cores, per_codeword_s=single,
+                ms_per_step=1e3 * wall / max(steps, 1))
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_run(args.steps, args.warmup)
+    kind = "port"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "codewords/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "info_mbit_per_s": res["value"] * INFO_BITS / 1e6,
+        "config": {"workload": WORKLOAD, "codewords_per_step": res["cores"]},
+        "cpu_baseline": {"value": res["value"], "unit": "codewords/s", "cores": res["cores"], "kind": kind,
+                         "sample": "%d steps x 1 soft-flow codeword per worker on %d workers (%.1f s per codeword per "
+                                   "core); oracle port of the reference algorithm (numpy + C w-point FHT, C BP)"
+                                   % (args.steps, res["cores"], res["per_codeword_s"])},
+        "e2e": {"value": res["value"], "unit": "codewords/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ clocks sampler
+class Clocks(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    from sparc_ldpc_b200 import _lib, decoder as D, engine as E, sparc_ldpc as S
+    from sparc_ldpc_b200.ldpc import get_code
+
+    B = args.batch
+    sp = S.SPARCParams(L=L, M=M, sigma=SIGMA, p=P, r=R_SPARC, t=T)
+    su = D.make_setup(sp, S.LDPCParams(STD, RATE, Z))
+    assert su.n == N and su.total_bits - (su.nl - su.kl) == INFO_BITS
+
+    # synthetic codewords: valid LDPC codewords + AWGN from a per-rank seeded host stream (reference draw order)
+    rng = np.random.RandomState(1000 + rank)
+    idx, noise = S._draw(su, B, SIGMA, rng)
+    tx = torch.from_numpy(idx).to(dev)
+    y_dev = su.op.onehot_apply(tx, su.Pl_dev) + torch.from_numpy(noise).to(dev)
+    y_host = y_dev.cpu().pin_memory()
+    idx_host = torch.empty((B, L), dtype=torch.int32).pin_memory()
+    errs_host = torch.empty((2 * SOFT_ITER + 1, B), dtype=torch.int32).pin_memory()
+    torch.cuda.synchronize()
+
+    amp_events, amp_meta = [], []
+    orig_amp = su.op.amp
+
+    def timed_amp(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_amp(*a, **k)
+        e1.record()
+        amp_events.append((e0, e1))
+        amp_meta.append(r.n_exec)
+        return r
+
+    def step_device(y):
+        st = D.soft(su, y, SOFT_ITER)
+        stages = [st.amp_idx[0]]
+        for i in range(SOFT_ITER):
+            stages += [st.ldpc_idx[i], st.amp_idx[i + 1]]
+        errs = torch.stack([E.count_errors(s, tx) for s in stages])          # [5, B] bit errors per stage
+        totals = errs.sum(dim=1, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(totals)                                           # the path's only collective
+        return st, errs, totals
+
+    def step_e2e():
+        y = y_host.to(dev, non_blocking=True)
+        st, errs, totals = step_device(y)
+        idx_host.copy_(st.ldpc_idx[-1], non_blocking=True)                   # final decisions
+        errs_host.copy_(errs, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return totals
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        step_device(y_dev)
+    barrier()
+
+    # ---- timed: device-resident inputs
+    su.op.amp = timed_amp
+    clocks = Clocks(local)
+    clocks.start()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    bp_its, last = [], None
+    for _ in range(args.steps):
+        last = step_device(y_dev)
+        bp_its.append(last[0].bp_it)
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    su.op.amp = orig_amp
+    amp_ms = sum(a.elapsed_time(b) for a, b in amp_events)
+    n_amp_launch = len(amp_events)
+    exec_iters = float(sum(int(m.sum()) for m in amp_meta))
+    bp_iters = float(sum(int(t.sum()) for its in bp_its for t in its))
+    amp_events.clear()
+
+    # ---- timed: end to end from pinned host buffers
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    clocks.stop_flag.set()
+    clocks.join(2)
+
+    t = torch.tensor([ms, ms_e2e, amp_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([exec_iters, bp_iters], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums)
+    ms, ms_e2e, amp_ms = (float(v) for v in t)
+    exec_iters, bp_iters = (float(v) for v in sums)
+
+    total_cw = B * world * args.steps
+    value = total_cw / (ms / 1e3)
+    e2e = total_cw / (ms_e2e / 1e3)
+    peak, peak_src = peak_hbm()
+    bytes_per_iter = (2 * L * M + 3 * N) * 8                    # read beta + write beta + read y, read z, write z (fp64)
+    alg_bytes = exec_iters * bytes_per_iter / world             # per rank (ranks run concurrently)
+    achieved = alg_bytes / (amp_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "amp_traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    if rank == 0:
+        errs_tot = last[2].cpu().numpy()
+        nbits = B * world * su.total_bits
+        line = {
+            "metric": METRIC, "value": value, "unit": "codewords/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "info_mbit_per_s": value * INFO_BITS / 1e6,
+            "config": {"workload": WORKLOAD, "codewords_per_step_per_gpu": B, "sigma": SIGMA, "amp_T": T,
+                       "l2": "working set %.0f MB of beta per GPU per step exceeds the 126 MB L2" % (B * L * M * 8 / 1e6),
+                       "ber_per_stage[amp1,ldpc1,amp2,ldpc2,amp3]": (errs_tot / nbits).tolist(),
+                       "mean_amp_iterations_per_decode": exec_iters / (3.0 * total_cw),
+                       "mean_bp_iterations_per_decode": bp_iters / (2.0 * total_cw)},
+            "e2e": {"value": e2e, "unit": "codewords/s", "h2d_bytes_per_step": int(B * N * 8),
+                    "d2h_bytes_per_step": int(idx_host.numel() * 4 + errs_host.numel() * 4),
+                    "info_mbit_per_s": e2e * INFO_BITS / 1e6},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "sb::amp_kernel<9>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_codeword_iteration": bytes_per_iter,
+                         "launches_timed": n_amp_launch, "kernel_share_of_step": amp_ms / ms,
+                         "avg_launch_ms": amp_ms / max(n_amp_launch, 1)},
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                c = cpu_run(1, 0)
+                line["cpu_baseline"] = {"value": c["value"], "unit": "codewords/s", "cores": c["cores"], "kind": "port",
+                                        "sample": "1 soft-flow codeword per worker on %d workers (%.1f s per codeword per core); "
+                                                  "oracle port of the reference algorithm" % (c["cores"], c["per_codeword_s"])}
+            except Exception as ex:  # the baseline is reported, never the product path
+                line["cpu_baseline"] = {"value": None, "unit": "codewords/s", "cores": 0, "kind": "port", "sample": "failed: %r" % ex}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=296, help="codewords per step per GPU (2 x 148 SMs)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -303,6 +303,8 @@ def gen_flows():
         d[tag + "_res"] = np.array(rows)
         d[tag + "_n_amp"] = len(cap.amp_calls)
         d[tag + "_n_dec"] = len(cap.dec_calls)
+        # BP iteration counts of every decode call, per repetition (200 = did not converge: chaotic orbit)
+        d[tag + "_its"] = np.array([c["it"] for c in cap.dec_calls]).reshape(reps, -1) if cap.dec_calls else np.zeros((reps, 0), dtype=int)
         # first codeword's captured calls (small sizes: keep everything)
         for j, c in enumerate(cap.amp_calls[: len(cap.amp_calls) // reps]):
             d["%s_amp%d_y" % (tag, j)], d["%s_amp%d_out" % (tag, j)] = c["y"], c["out"]
