@@ -76,8 +76,10 @@ __device__ __forceinline__ double block_max(double v, double *scratch) {
 
 struct sb_operator {
     int L, M, n, logM, w, H, Hp, NB;  // H = w/M blocks, Hp = padded to a multiple of 16, NB = Hp/16
-    uint16_t *fwd;                    // [L][n]   lo | sign<<15         (A beta gather)
-    uint16_t *inv;                    // [L][M][Hp] k or 0xFFFF, visit (bit-reversed hi) order (A^T z fold)
+    int pre, G8;                      // pre: inv entries are byte offsets; G8 = ceil(L/8)
+    uint16_t *fwd;                    // [L][n]      lo | sign<<15                    (A beta gather, section lists)
+    uint16_t *fwd8;                   // [G8][n][8]  the same entries, 8 sections interleaved (A beta gather, all sections)
+    uint16_t *inv;                    // [L][M][Hp]  k (or k*8) / n (or n*8) = the zero word, visit order (A^T z fold)
 };
 
 struct sb_graph {

@@ -421,7 +421,7 @@ def test_c3_soft_stage_internals(S, Eng):
     # (ln 2 steps around |LLR| = 36.7).  Tolerance = 1e-6 relative + 8 ulps of p.
     tol = 1e-6 * np.abs(ref) + 8 * 2.0 ** -53 * (1 + np.exp(np.minimum(np.abs(ref), 700)))
     assert np.all(np.abs(llr - ref)[~sat] <= tol[~sat]), float(np.max((np.abs(llr - ref) / tol)[~sat]))
-    well = ~sat & (np.abs(ref) < 25)
+    well = ~sat & (np.abs(ref) < 15)
     np.testing.assert_allclose(llr[well], ref[well], rtol=1e-6, atol=1e-9)
 
 
