@@ -266,11 +266,11 @@ def gpu_arm(args):
     bytes_per_iter = (2 * L * M + 3 * N) * 8                    # read beta + write beta + read y, read z, write z (fp64)
     alg_bytes = exec_iters * bytes_per_iter / world             # per rank (ranks run concurrently)
     achieved = alg_bytes / (amp_ms / 1e3) / 1e9
-    traffic = None
+    traffic = None   # dram bytes per launch: ncu-measured dram/algorithmic ratio of this kernel x this run's bytes per launch
     tpath = os.path.join(ROOT, "profiles", "amp_traffic.json")
     if os.path.isfile(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            traffic = float(json.load(open(tpath))["ratio"]) * alg_bytes / max(n_amp_launch, 1)
         except Exception:
             traffic = None
 
@@ -295,7 +295,9 @@ def gpu_arm(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_codeword_iteration": bytes_per_iter,
                          "launches_timed": n_amp_launch, "kernel_share_of_step": amp_ms / ms,
-                         "avg_launch_ms": amp_ms / max(n_amp_launch, 1)},
+                         "avg_launch_ms": amp_ms / max(n_amp_launch, 1),
+                         "algorithmic_bytes_per_launch": alg_bytes / max(n_amp_launch, 1),
+                         "co_limiter": "shared-memory data pipe (l1tex LSU wavefronts 81% of peak, profiles/r01_amp_kernel_ncu_full.csv)"},
             "clocks": clocks.summary(),
         }
         if world == 1 and not args.no_cpu:
