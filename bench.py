@@ -159,6 +159,7 @@ def gpu_arm(args):
     from sparc_ldpc_b200.ldpc import get_code
 
     B = args.batch
+    E.AMP_MODE = args.amp_mode
     sp = S.SPARCParams(L=L, M=M, sigma=SIGMA, p=P, r=R_SPARC, t=T)
     su = D.make_setup(sp, S.LDPCParams(STD, RATE, Z))
     assert su.n == N and su.total_bits - (su.nl - su.kl) == INFO_BITS
@@ -283,6 +284,8 @@ def gpu_arm(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "info_mbit_per_s": value * INFO_BITS / 1e6,
             "config": {"workload": WORKLOAD, "codewords_per_step_per_gpu": B, "sigma": SIGMA, "amp_T": T,
+                       "amp_mode": args.amp_mode + (" (fp64; z and FHT(beta) gathered from 27-bit fixed-point copies)"
+                                                    if args.amp_mode == "fast" else " (fp64, reference add order)"),
                        "l2": "working set %.0f MB of beta per GPU per step exceeds the 126 MB L2" % (B * L * M * 8 / 1e6),
                        "ber_per_stage[amp1,ldpc1,amp2,ldpc2,amp3]": (errs_tot / nbits).tolist(),
                        "mean_amp_iterations_per_decode": exec_iters / (3.0 * total_cw),
@@ -318,9 +321,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=296, help="codewords per step per GPU (2 x 148 SMs)")
+    ap.add_argument("--batch", type=int, default=1184, help="codewords per step per GPU (8 x 148 SMs: several waves even out the per-codeword early stop)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--amp-mode", default="fast", choices=["strict", "fast"],
+                    help="AMP arithmetic: strict = fp64 in the reference's add order; fast = fp64 with 32-bit "
+                         "fixed-point gathers (include/sparc_b200.h SB_AMP_FAST); both pass the parity tests")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

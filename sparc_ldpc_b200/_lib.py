@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libsparc_b200.so")
 
 SB_BP_SUMPROD2, SB_BP_SUMPROD, SB_BP_MINSUM = 0, 1, 2
 SB_AMP_STOPPED, SB_AMP_REF_NAN = 1, 2
+SB_AMP_STRICT, SB_AMP_FAST = 0, 1
 SB_MAX_ITCOUNT = 200
 
 _lib = None
@@ -37,7 +38,7 @@ SIGNATURES = {
     "sb_Ab_batch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "sb_Az_batch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "sb_onehot_apply_batch": (_i, [_vp, _vp, _vp, _vp, _d, _i, _vp, _vp]),
-    "sb_amp_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_amp_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_sp2bp_llr_batch": (_i, [_vp, _l, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _l, _vp]),
     "sb_bp2sp_prior_batch": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "sb_argmax_batch": (_i, [_vp, _l, _i, _i, _i, _vp, _l, _vp]),

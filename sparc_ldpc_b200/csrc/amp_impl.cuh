@@ -1,0 +1,632 @@
+// amp_impl.cuh -- SPARC design operator and AMP decoder kernels (sm_100a), templated on the section size.
+//
+// Replaces ldpc/sparc_ldpc.py:32-147 (sub_fht / block_sub_fht / sparc_transforms[_shorter]) and
+// :189-222 (amp) of the reference.  The reference zero-pads every section to w = 2^ceil(log2(n+1))
+// and runs a w-point Walsh-Hadamard transform; because only the last M columns of H_w are used,
+//     (A beta)[k]  = (1/sqrt n) sum_l sgn(l,k) * FHT_M(beta_l)[lo(l,k)]
+//     (A^T z)_l    = (1/sqrt n) FHT_M(fold_l(z)),
+// with r = ordering[l][k], lo = r mod M, hi = r div M, sgn = (-1)^popcount(hi) and fold_l the signed
+// butterfly tree over the w/M blocks.  In STRICT mode both identities are evaluated in the reference's
+// own order of additions (fold tree = order of the large-stride butterflies, M-point stages from stride
+// M/2 down to 1, sections accumulated into A beta in ascending order, sparc_ldpc.py:123-126), which makes
+// Ab / Az bit-identical to the reference.
+//
+// Kernel structure: ONE persistent CTA per codeword runs the whole AMP loop (all T iterations) in a
+// single launch.  z and the A beta accumulator live in shared memory; beta streams through HBM once in
+// and once out per iteration (the section-wise softmax needs only the section itself); the lookup tables
+// are shared by the whole batch and stay L2-resident:
+//     inv  u16 [L][M][Hp]   for bin lo of section l: the k (as k*4) of every block, in the visit order of the
+//                           fold tree; empty blocks point at a zero word
+//     fwd  u16 [L][n]       for row k of section l: lo*4 | sgn << SBQ   (section lists)
+//     fwd8 u16 [L/8][n][8]  the same entries with 8 sections interleaved: one 16-byte load per (group, k)
+// Per group of W sections each team (<= one warp) transforms one section and leaves FHT_M(beta_l) in shared
+// memory TWICE, as +F and as -F, so that the signed gather of A beta is one LDS at offset (entry) and one add.
+//
+// The kernel is bound by the shared-memory data pipe: 2*L*n random accesses per codeword-iteration.  QUANT
+// mode therefore keeps 32-bit fixed-point copies of the two randomly gathered vectors: z (27 bits below its
+// per-iteration power-of-two ceiling) and F (27 bits below the ceiling of sqrt(n P_l)); fold and gather
+// become exact integer adds, everything else (FHT, softmax, z update, tau^2) stays fp64.  The only error is
+// the rounding of z and F to 2^-27 of their range (relative effect on beta ~1e-8, tolerance 1e-5).
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+__host__ __device__ __forceinline__ int pad2(int n) { return (n + 1) & ~1; }
+__host__ __device__ __forceinline__ int pad4(int n) { return (n + 3) & ~3; }
+
+template <int LOGM>
+struct TeamCfg {
+    static constexpr int M = 1 << LOGM;
+    static constexpr int TEAM = (M >= 128) ? 32 : (M >= 4 ? M / 4 : 1);  // lanes cooperating on one section
+    static constexpr int EPT = M / TEAM;                                  // elements per lane
+    static constexpr int SPR = (LOGM >= 10) ? 4 : 8;                      // section slots per F region
+    static constexpr int SBQ = LOGM + 2 + ((LOGM >= 10) ? 2 : 3);         // sign bit of a fwd entry (<= 14)
+};
+
+// byte offset of section slot `slot` (+F copy) inside the F area; ESH = log2(element bytes) (3: fp64, 2: int32)
+template <int LOGM, int ESH>
+__device__ __forceinline__ int slot_offset(int slot) {
+    using C = TeamCfg<LOGM>;
+    return (slot / C::SPR) * (2 << (C::SBQ + ESH - 2)) + (slot % C::SPR) * (C::M << ESH);
+}
+
+// shuffle mask of the calling lane's team (teams of one warp may diverge from each other)
+template <int TEAM>
+__device__ __forceinline__ unsigned team_mask() {
+    if constexpr (TEAM >= 32) {
+        return 0xffffffffu;
+    } else {
+        return ((1u << TEAM) - 1u) << (((threadIdx.x & 31) / TEAM) * TEAM);
+    }
+}
+
+// M-point Walsh-Hadamard transform of one section held by a team: element j = e*TEAM + q lives in
+// x[e] of team lane q.  Stage order = strides M/2 ... 1 (ldpc/sparc_ldpc.py:19-29): (a, b) -> (a+b, a-b).
+template <int LOGM>
+__device__ __forceinline__ void fht_team(double (&x)[TeamCfg<LOGM>::EPT], int q, unsigned tmask) {
+    constexpr int TEAM = TeamCfg<LOGM>::TEAM, EPT = TeamCfg<LOGM>::EPT;
+#pragma unroll
+    for (int s = EPT / 2; s >= 1; s >>= 1) {
+#pragma unroll
+        for (int i = 0; i < EPT; i++) {
+            if ((i & s) == 0) {
+                double a = x[i], b = x[i + s];
+                x[i] = a + b;
+                x[i + s] = a - b;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = TEAM / 2; d >= 1; d >>= 1) {
+        // lane with bit d set holds x[ij]: new = partner - mine = partner + (-mine); negation = sign-bit xor
+        const int sgn = (q & d) ? (int)0x80000000 : 0;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const double p = __shfl_xor_sync(tmask, x[e], d);
+            const double mine = __hiloint2double(__double2hiint(x[e]) ^ sgn, __double2loint(x[e]));
+            x[e] = p + mine;
+        }
+    }
+}
+
+// z value addressed by an inverse-table entry e.  PRE: e = k*4 (byte offset of an int32), else e = k.
+template <bool PRE, typename T>
+__device__ __forceinline__ T zs_at(const T *zs, uint32_t e) {
+    if (PRE) return *reinterpret_cast<const T *>(reinterpret_cast<const char *>(zs) + (sizeof(T) == 8 ? (e << 1) : e));
+    return zs[e];
+}
+
+// One block of 16 inverse-table entries in visit order; every tree node is (left - right), i.e.
+// v <- v[:half] - v[half:] of the reference's large-stride butterflies.  Empty slots point at zs[n] = 0.
+template <bool PRE, typename T>
+__device__ __forceinline__ T fold16(const uint4 p0, const uint4 p1, const T *zs) {
+    const uint32_t wds[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    T v[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        v[2 * i] = zs_at<PRE, T>(zs, wds[i] & 0xFFFFu);
+        v[2 * i + 1] = zs_at<PRE, T>(zs, wds[i] >> 16);
+    }
+#pragma unroll
+    for (int s = 1; s < 16; s <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2 * s) v[i] = v[i] - v[i + s];
+    }
+    return v[0];
+}
+
+// One bin with NB > 1 blocks: binary-counter merge (in fp64) of the block subtrees (left - right at every level).
+template <bool PRE, typename T>
+__device__ __forceinline__ double fold_bin_multi(const uint16_t *__restrict__ tab, int NB, const T *zs, double unit) {
+    double st[8];
+    double val = 0.0;
+    for (int c = 0; c < NB; c++) {
+        const uint4 p0 = __ldg(reinterpret_cast<const uint4 *>(tab + c * 16));
+        const uint4 p1 = __ldg(reinterpret_cast<const uint4 *>(tab + c * 16 + 8));
+        val = (double)fold16<PRE, T>(p0, p1, zs) * unit;
+        int cc = c, lvl = 0;
+#pragma unroll
+        for (int l = 0; l < 7; l++) {
+            if (cc & 1) {
+                val = st[l] - val;
+                cc >>= 1;
+                lvl = l + 1;
+            } else {
+                break;
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < 8; l++)
+            if (l == lvl) st[l] = val;
+    }
+    return val;
+}
+
+// fold_l(z) for the EPT bins of this lane, in units of `unit` (1.0 for fp64 z, 2^-zshift for fixed-point z).
+// NB == 1 (w/M <= 16, the headline shapes): the two 16-byte table loads of bin e+1 are issued before bin e
+// is reduced.
+template <int LOGM, bool PRE, typename T>
+__device__ __forceinline__ void fold_section(double (&x)[TeamCfg<LOGM>::EPT], const uint16_t *__restrict__ tab,
+                                             int Hp, int NB, int q, const T *zs, double unit) {
+    constexpr int TEAM = TeamCfg<LOGM>::TEAM, EPT = TeamCfg<LOGM>::EPT;
+    if (NB == 1) {
+        const uint4 *t4 = reinterpret_cast<const uint4 *>(tab);  // Hp == 16: two uint4 per bin
+        uint4 c0 = __ldg(t4 + 2 * q), c1 = __ldg(t4 + 2 * q + 1);
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            uint4 n0 = c0, n1 = c1;
+            if (e + 1 < EPT) {
+                n0 = __ldg(t4 + 2 * ((e + 1) * TEAM + q));
+                n1 = __ldg(t4 + 2 * ((e + 1) * TEAM + q) + 1);
+            }
+            if (sizeof(T) == 8)
+                x[e] = (double)fold16<PRE, T>(c0, c1, zs);
+            else
+                x[e] = (double)fold16<PRE, T>(c0, c1, zs) * unit;
+            c0 = n0;
+            c1 = n1;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < EPT; e++)
+            x[e] = fold_bin_multi<PRE, T>(tab + (size_t)(e * TEAM + q) * Hp, NB, zs, sizeof(T) == 8 ? 1.0 : unit);
+    }
+}
+
+struct AmpArgs {
+    const uint16_t *fwd, *fwd8, *inv;
+    const double *y, *Pl, *beta0;
+    const int *sections, *nsec;
+    double *beta, *tau2_trace;
+    int *iters, *n_exec;
+    unsigned *flags;
+    int L, n, Hp, NB, T;
+};
+
+struct SecCtx {  // per-iteration scalars of the section phase
+    double inv_rt_n, tau2, zunit, fscale;
+};
+
+// mode 0: AMP iteration (fold -> FHT -> softmax -> store beta -> FHT -> +-F)
+// mode 1: operator only (load beta -> FHT -> +-F), always fp64   [prologue z = y - A beta0, sb_Ab_batch]
+template <int LOGM, bool PRE, bool QUANT>
+__device__ __forceinline__ void section_phase(int mode, bool first_zero, const AmpArgs &a, const double *bsrc,
+                                              double *bdst, int sec, int q, const void *zsv, char *Fbytes, int slot,
+                                              const SecCtx &cx, double rt_npl, double &sq, double &gmax, double &lmin) {
+    constexpr int M = TeamCfg<LOGM>::M, TEAM = TeamCfg<LOGM>::TEAM, EPT = TeamCfg<LOGM>::EPT;
+    constexpr int SBQ = TeamCfg<LOGM>::SBQ;
+    double x[EPT];
+    const unsigned tmask = team_mask<TEAM>();
+    if (mode == 0) {
+        const uint16_t *tab = a.inv + ((size_t)sec * M) * a.Hp;
+        if (QUANT)
+            fold_section<LOGM, PRE, int>(x, tab, a.Hp, a.NB, q, static_cast<const int *>(zsv), cx.zunit);
+        else
+            fold_section<LOGM, PRE, double>(x, tab, a.Hp, a.NB, q, static_cast<const double *>(zsv), 1.0);
+        fht_team<LOGM>(x, q, tmask);
+        const double c2 = rt_npl / cx.tau2;
+        double m = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const double b = first_zero ? 0.0 : bsrc[e * TEAM + q];
+            const double s = b + x[e] * cx.inv_rt_n;  // s = beta + A^T z          (sparc_ldpc.py:213)
+            x[e] = s * c2;                            // u = s sqrt(n P_l)/tau^2    (:215)
+            m = fmax(m, x[e]);
+        }
+#pragma unroll
+        for (int d = TEAM / 2; d >= 1; d >>= 1) m = fmax(m, __shfl_xor_sync(tmask, m, d));
+        gmax = fmax(gmax, m);
+        lmin = fmin(lmin, m);
+        double sum = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            x[e] = exp(x[e] - m);  // section max instead of the reference's global max (:216): same softmax
+            sum += x[e];
+        }
+#pragma unroll
+        for (int d = TEAM / 2; d >= 1; d >>= 1) sum += __shfl_xor_sync(tmask, sum, d);
+        const double sc = rt_npl / sum;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            x[e] *= sc;  // beta = sqrt(n P_l) softmax(u)    (:218-219)
+            sq += x[e] * x[e];
+            bdst[e * TEAM + q] = x[e];
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            x[e] = bsrc[e * TEAM + q];
+            if (bdst != nullptr) bdst[e * TEAM + q] = x[e];
+        }
+    }
+    fht_team<LOGM>(x, q, tmask);
+    if (QUANT && mode == 0) {
+        int *Fp = reinterpret_cast<int *>(Fbytes + slot_offset<LOGM, 2>(slot));
+        int *Fn = reinterpret_cast<int *>(Fbytes + slot_offset<LOGM, 2>(slot) + (1 << SBQ));
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const int f = __double2int_rn(x[e] * cx.fscale);
+            Fp[e * TEAM + q] = f;
+            Fn[e * TEAM + q] = -f;
+        }
+    } else {
+        double *Fp = reinterpret_cast<double *>(Fbytes + slot_offset<LOGM, 3>(slot));
+        double *Fn = reinterpret_cast<double *>(Fbytes + slot_offset<LOGM, 3>(slot) + (2 << SBQ));
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            Fp[e * TEAM + q] = x[e];
+            Fn[e * TEAM + q] = -x[e];
+        }
+    }
+}
+
+// signed F value addressed by a fwd entry (lo*4 | sgn << SBQ) relative to the slot's +F copy
+template <typename T>
+__device__ __forceinline__ T F_at(const char *slot_base, uint32_t e) {
+    return *reinterpret_cast<const T *>(slot_base + (sizeof(T) == 8 ? (e << 1) : e));
+}
+
+// acc[k] += sum over the group's sections (ascending) of sgn * F[lo]     (sparc_ldpc.py:123-126, :70)
+// generic section lists: one u16 row per section.  T = double (strict) or int (fixed point, flushed to fp64
+// every 16 sections so that the int32 partial sums cannot overflow).
+template <int LOGM, typename T>
+__device__ __forceinline__ void gather_phase(const uint16_t *__restrict__ fwd, int n, int nvalid, const int *sec_s,
+                                             const char *Fbytes, double *acc_s, double funit) {
+    constexpr int ESH = sizeof(T) == 8 ? 3 : 2;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        double acc = acc_s[k];
+        T part = 0;
+        int tm = 0;
+        for (; tm + 4 <= nvalid; tm += 4) {
+            uint32_t e[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) e[i] = __ldg(fwd + (size_t)sec_s[tm + i] * n + k);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const T v = F_at<T>(Fbytes + slot_offset<LOGM, ESH>(tm + i), e[i]);
+                if (sizeof(T) == 8) acc += v; else part += v;
+            }
+            if (sizeof(T) != 8 && ((tm + 4) & 15) == 0) {
+                acc += (double)part * funit;
+                part = 0;
+            }
+        }
+        for (; tm < nvalid; tm++) {
+            const T v = F_at<T>(Fbytes + slot_offset<LOGM, ESH>(tm), __ldg(fwd + (size_t)sec_s[tm] * n + k));
+            if (sizeof(T) == 8) acc += v; else part += v;
+        }
+        if (sizeof(T) != 8) acc += (double)part * funit;
+        acc_s[k] = acc;
+    }
+}
+
+// all sections in order and groups aligned to 8: the 8 entries of (group, k) are one 16-byte load from the
+// interleaved table.  KB rows per thread are in flight together and chunk c+1 is loaded while chunk c is used.
+template <int LOGM, typename T>
+__device__ __forceinline__ void gather_phase8(const uint16_t *__restrict__ fwd8, int n, int g0, int nvalid,
+                                              const char *Fbytes, double *acc_s, double funit) {
+    constexpr int KB = 4;
+    constexpr int ESH = sizeof(T) == 8 ? 3 : 2;
+    const uint4 *tab = reinterpret_cast<const uint4 *>(fwd8) + (size_t)(g0 >> 3) * n;
+    const int nch = (nvalid + 7) >> 3, NT = blockDim.x;
+    for (int k0 = threadIdx.x; k0 < n; k0 += KB * NT) {
+        double acc[KB];
+        T part[KB];
+        uint4 w[KB];
+#pragma unroll
+        for (int j = 0; j < KB; j++) {
+            const int k = k0 + j * NT;
+            acc[j] = (k < n) ? acc_s[k] : 0.0;
+            part[j] = 0;
+            w[j] = (k < n) ? __ldg(tab + k) : make_uint4(0, 0, 0, 0);
+        }
+        for (int c = 0; c < nch; c++) {
+            uint4 wn[KB];
+#pragma unroll
+            for (int j = 0; j < KB; j++) {
+                const int k = k0 + j * NT;
+                wn[j] = (c + 1 < nch && k < n) ? __ldg(tab + (size_t)(c + 1) * n + k) : make_uint4(0, 0, 0, 0);
+            }
+            const char *F = Fbytes + slot_offset<LOGM, ESH>(c * 8);  // c*8 is a multiple of SPR: region start
+            const bool full = (c * 8 + 8 <= nvalid);
+            const bool flush = (sizeof(T) != 8) && ((c & 1) == 1 || c + 1 == nch);  // <= 16 int32 terms per flush
+#pragma unroll
+            for (int j = 0; j < KB; j++) {
+                const uint32_t wds[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (full || c * 8 + i < nvalid) {
+                        const uint32_t e = (i & 1) ? (wds[i >> 1] >> 16) : (wds[i >> 1] & 0xFFFFu);
+                        const T v = F_at<T>(F + slot_offset<LOGM, ESH>(i), e);
+                        if (sizeof(T) == 8) acc[j] += v; else part[j] += v;
+                    }
+                }
+                if (flush) {
+                    acc[j] += (double)part[j] * funit;
+                    part[j] = 0;
+                }
+                w[j] = wn[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KB; j++) {
+            const int k = k0 + j * NT;
+            if (k < n) acc_s[k] = acc[j];
+        }
+    }
+}
+
+// One pass over all active sections: section_phase per team, then the gather per group.
+template <int LOGM, bool PRE, bool QUANT>
+__device__ __forceinline__ void operator_pass(int mode, bool first_zero, const AmpArgs &a, const double *bsrc,
+                                              double *bdst, const int *act, int La, const void *zsv, double *acc_s,
+                                              char *Fbytes, int *sec_s, int W, const SecCtx &cx, double nd, double &sq,
+                                              double &gmax, double &lmin) {
+    constexpr int M = TeamCfg<LOGM>::M, TEAM = TeamCfg<LOGM>::TEAM;
+    const int tm = threadIdx.x / TEAM, q = threadIdx.x % TEAM;
+    const bool qpass = QUANT && mode == 0;
+    for (int k = threadIdx.x; k < a.n; k += blockDim.x) acc_s[k] = 0.0;
+    for (int g0 = 0; g0 < La; g0 += W) {
+        const int sidx = g0 + tm;
+        const bool valid = (tm < W) && (sidx < La);
+        const int sec = valid ? (act ? act[sidx] : sidx) : 0;
+        if (q == 0 && tm < W) sec_s[tm] = sec;
+        if (valid) {
+            const double rt_npl = sqrt(nd * a.Pl[sec]);
+            section_phase<LOGM, PRE, QUANT>(mode, first_zero, a, bsrc ? bsrc + (size_t)sidx * M : nullptr,
+                                            bdst ? bdst + (size_t)sidx * M : nullptr, sec, q, zsv, Fbytes, tm, cx,
+                                            rt_npl, sq, gmax, lmin);
+        }
+        __syncthreads();
+        const int nvalid = min(W, La - g0);
+        const bool fast = (act == nullptr && (W & 7) == 0);
+        const double funit = 1.0 / cx.fscale;
+        if (qpass) {
+            if (fast) gather_phase8<LOGM, int>(a.fwd8, a.n, g0, nvalid, Fbytes, acc_s, funit);
+            else gather_phase<LOGM, int>(a.fwd, a.n, nvalid, sec_s, Fbytes, acc_s, funit);
+        } else {
+            if (fast) gather_phase8<LOGM, double>(a.fwd8, a.n, g0, nvalid, Fbytes, acc_s, 1.0);
+            else gather_phase<LOGM, double>(a.fwd, a.n, nvalid, sec_s, Fbytes, acc_s, 1.0);
+        }
+        __syncthreads();
+    }
+}
+
+// shared-memory carve-up.  strict: z fp64 [n+1 (zero word)] | acc | F | red | sec
+//                          quant : zq int32 [n+1 (zero word)] | z fp64 [n] | acc | F (fp64-sized: prologue) | red | sec
+template <int LOGM, bool QUANT>
+struct Smem {
+    double *zf, *acc, *red;
+    int *zq;
+    char *F;
+    int *sec;
+    __host__ __device__ static size_t f_bytes(int W) {
+        const int regions = (W + TeamCfg<LOGM>::SPR - 1) / TeamCfg<LOGM>::SPR;
+        return (size_t)regions * (4 << TeamCfg<LOGM>::SBQ);
+    }
+    __host__ __device__ static size_t bytes(int n, int W) {
+        size_t b = QUANT ? sizeof(int) * (size_t)pad4(n + 1) + sizeof(double) * (size_t)pad2(n)
+                         : sizeof(double) * (size_t)pad2(n + 1);
+        b += sizeof(double) * (size_t)pad2(n);  // acc
+        b += f_bytes(W);
+        b += sizeof(double) * 40 + sizeof(int) * (size_t)(W + 2);
+        return b;
+    }
+    __device__ Smem(unsigned char *raw, int n, int W) {
+        if (QUANT) {
+            zq = reinterpret_cast<int *>(raw);
+            zf = reinterpret_cast<double *>(zq + pad4(n + 1));
+            acc = zf + pad2(n);
+        } else {
+            zq = nullptr;
+            zf = reinterpret_cast<double *>(raw);
+            acc = zf + pad2(n + 1);
+        }
+        F = reinterpret_cast<char *>(acc + pad2(n));
+        red = reinterpret_cast<double *>(F + f_bytes(W));
+        sec = reinterpret_cast<int *>(red + 40);
+    }
+};
+
+// power-of-two ceiling exponent: smallest e with |v| < 2^e  (v > 0 finite)
+__device__ __forceinline__ int ceil_exp(double v) { return (v > 0.0) ? ilogb(v) + 1 : 0; }
+
+template <int LOGM, bool PRE, bool QUANT>
+__global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
+    constexpr int M = TeamCfg<LOGM>::M;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, b = blockIdx.x;
+    Smem<LOGM, QUANT> sm(smem_raw, n, W);
+    double *zf = sm.zf, *acc_s = sm.acc, *red = sm.red;
+    if (threadIdx.x == 0) {
+        if (QUANT) sm.zq[n] = 0; else zf[n] = 0.0;
+    }
+    const void *zsv = QUANT ? static_cast<const void *>(sm.zq) : static_cast<const void *>(zf);
+
+    const int La = a.nsec ? a.nsec[b] : a.L;
+    const int *act = a.sections ? a.sections + (size_t)b * a.L : nullptr;
+    const double *y = a.y + (size_t)b * n;
+    double *beta = a.beta + (size_t)b * a.L * M;
+    const double nd = (double)n;
+    const double rt_n = sqrt(nd);
+    double sq = 0.0, gmax = -INFINITY, lmin = INFINITY;
+    SecCtx cx;
+    cx.inv_rt_n = 1.0 / rt_n;
+    cx.tau2 = 1.0;
+    cx.zunit = 1.0;
+    cx.fscale = 1.0;
+
+    if (La <= 0) {  // the reference never calls amp() on an empty section set (sparc_ldpc.py:1015)
+        if (threadIdx.x == 0) {
+            a.iters[b] = 0;
+            a.n_exec[b] = 0;
+            a.flags[b] = 0;
+        }
+        return;
+    }
+
+    // P = sum of the active sections' power (np.sum(Pl), sparc_ldpc.py:190); cmax bounds |FHT_M(beta_l)|
+    double pl = 0.0, plmax = 0.0;
+    for (int i = threadIdx.x; i < La; i += blockDim.x) {
+        const double p = a.Pl[act ? act[i] : i];
+        pl += p;
+        plmax = fmax(plmax, p);
+    }
+    const double P = block_sum(pl, red);
+    const double cmax = sqrt(nd * block_max(plmax, red));
+    // |F| <= sqrt(n P_l) <= cmax; the 1e-6 margin keeps |F_q| strictly below 2^27 so 16-term int32 sums cannot overflow
+    const double fscale_q = scalbn(1.0, 27 - ceil_exp(cmax * (1.0 + 1e-6)));
+
+    if (a.beta0 != nullptr) {  // z = y - A beta0   (sparc_ldpc.py:197-198), always in fp64
+        operator_pass<LOGM, PRE, QUANT>(1, false, a, a.beta0 + (size_t)b * a.L * M, beta, act, La, zsv, acc_s, sm.F,
+                                        sm.sec, W, cx, nd, sq, gmax, lmin);
+        for (int k = threadIdx.x; k < n; k += blockDim.x) zf[k] = y[k] - acc_s[k] / rt_n;
+    } else {
+        for (int k = threadIdx.x; k < n; k += blockDim.x) zf[k] = y[k];
+    }
+    __syncthreads();
+
+    bool first_zero = (a.beta0 == nullptr);
+    double last_tau = 0.0;
+    unsigned flags = 0;
+    int t = 0, executed = 0;
+    for (t = 0; t < a.T; t++) {
+        double part = 0.0, zmax = 0.0;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            part += zf[k] * zf[k];
+            zmax = fmax(zmax, fabs(zf[k]));
+        }
+        const double tau = sqrt(block_sum(part, red) / nd);  // (:203)
+        if (tau == last_tau) {                               // exact-equality stop (:204)
+            flags |= SB_AMP_STOPPED;
+            break;
+        }
+        last_tau = tau;
+        cx.tau2 = tau * tau;
+        if (a.tau2_trace != nullptr && threadIdx.x == 0) a.tau2_trace[(size_t)b * a.T + t] = cx.tau2;
+        if (QUANT) {  // fixed-point copy of z: 27 bits below the power-of-two ceiling of max |z|
+            const int ez = ceil_exp(block_max(zmax, red) * (1.0 + 1e-6));
+            const double zscale = scalbn(1.0, 27 - ez);
+            cx.zunit = scalbn(1.0, ez - 27);
+            cx.fscale = fscale_q;
+            for (int k = threadIdx.x; k < n; k += blockDim.x) sm.zq[k] = __double2int_rn(zf[k] * zscale);
+            __syncthreads();
+        }
+        sq = 0.0;
+        gmax = -INFINITY;
+        lmin = INFINITY;
+        operator_pass<LOGM, PRE, QUANT>(0, first_zero, a, beta, beta, act, La, zsv, acc_s, sm.F, sm.sec, W, cx, nd, sq,
+                                        gmax, lmin);
+        first_zero = false;
+        const double sumsq = block_sum(sq, red);
+        const double gm = block_max(gmax, red);
+        const double lm = -block_max(-lmin, red);
+        if (gm - lm > 745.13) flags |= SB_AMP_REF_NAN;
+        const double ons = P - sumsq / nd;  // (:220)
+        for (int k = threadIdx.x; k < n; k += blockDim.x) zf[k] = (y[k] - acc_s[k] / rt_n) + (zf[k] / cx.tau2) * ons;
+        __syncthreads();
+        executed++;
+    }
+    if (first_zero) {  // T == 0 or stop before the first update: beta is the zero vector
+        for (int i = threadIdx.x; i < La * M; i += blockDim.x) beta[i] = 0.0;
+    }
+    if (threadIdx.x == 0) {
+        a.iters[b] = (t < a.T) ? t : (a.T > 0 ? a.T - 1 : 0);
+        a.n_exec[b] = executed;
+        a.flags[b] = flags;
+    }
+}
+
+// A_S beta for a batch (sparc_ldpc.py:143-144): out = acc / sqrt(n)   (always strict fp64)
+template <int LOGM, bool PRE>
+__global__ void __launch_bounds__(512, 1) Ab_kernel(AmpArgs a, int W, const double *beta_in, double *out) {
+    constexpr int M = TeamCfg<LOGM>::M;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, b = blockIdx.x;
+    Smem<LOGM, false> sm(smem_raw, n, W);
+    const int La = a.nsec ? a.nsec[b] : a.L;
+    const int *act = a.sections ? a.sections + (size_t)b * a.L : nullptr;
+    double sq = 0, gmax = 0, lmin = 0;
+    const double nd = (double)n, rt_n = sqrt(nd);
+    SecCtx cx;
+    cx.inv_rt_n = 1.0 / rt_n; cx.tau2 = 1.0; cx.zunit = 1.0; cx.fscale = 1.0;
+    operator_pass<LOGM, PRE, false>(1, false, a, beta_in + (size_t)b * a.L * M, nullptr, act, La, sm.zf, sm.acc, sm.F,
+                                    sm.sec, W, cx, nd, sq, gmax, lmin);
+    for (int k = threadIdx.x; k < n; k += blockDim.x) out[(size_t)b * n + k] = sm.acc[k] / rt_n;
+}
+
+// A_S^T z for a batch (sparc_ldpc.py:145-146): one team per section   (always strict fp64)
+template <int LOGM, bool PRE>
+__global__ void __launch_bounds__(512, 1) Az_kernel(AmpArgs a, int W, const double *z_in, double *out) {
+    constexpr int M = TeamCfg<LOGM>::M, TEAM = TeamCfg<LOGM>::TEAM, EPT = TeamCfg<LOGM>::EPT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, b = blockIdx.x;
+    const int NTM = blockDim.x / TEAM;
+    double *zs = reinterpret_cast<double *>(smem_raw);
+    const int La = a.nsec ? a.nsec[b] : a.L;
+    const int *act = a.sections ? a.sections + (size_t)b * a.L : nullptr;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) zs[k] = z_in[(size_t)b * n + k];
+    if (threadIdx.x == 0) zs[n] = 0.0;
+    __syncthreads();
+    const double rt_n = sqrt((double)n);
+    const int tm = threadIdx.x / TEAM, q = threadIdx.x % TEAM;
+    for (int sidx = tm; sidx < La; sidx += NTM) {  // whole teams leave together: shuffles stay converged
+        const int sec = act ? act[sidx] : sidx;
+        double x[EPT];
+        fold_section<LOGM, PRE, double>(x, a.inv + ((size_t)sec * M) * a.Hp, a.Hp, a.NB, q, zs, 1.0);
+        fht_team<LOGM>(x, q, team_mask<TEAM>());
+#pragma unroll
+        for (int e = 0; e < EPT; e++) out[(size_t)b * a.L * M + (size_t)sidx * M + e * TEAM + q] = x[e] / rt_n;
+    }
+}
+
+// threads per CTA: as many teams as fit in shared memory (<= 512 threads), never more teams than sections
+template <int LOGM, bool QUANT>
+static int pick_threads(int n, int L, size_t *smem_out, int *W_out) {
+    constexpr int TEAM = TeamCfg<LOGM>::TEAM;
+    int nt = 512;
+    const char *env = getenv("SB_AMP_THREADS");
+    if (env) nt = atoi(env);
+    if (nt > 512) nt = 512;
+    nt = (nt / 32) * 32;
+    if (nt < 32) nt = 32;
+    if (nt < TEAM) nt = TEAM;
+    while (nt > 64 && (nt / 2) / TEAM >= L) nt /= 2;
+    while (nt > 32 && nt > TEAM && Smem<LOGM, QUANT>::bytes(n, nt / TEAM) > 227 * 1024) nt /= 2;
+    *W_out = nt / TEAM;
+    *smem_out = Smem<LOGM, QUANT>::bytes(n, *W_out);
+    return nt;
+}
+
+// which: 0 = AMP strict, 1 = A beta, 2 = A^T z, 3 = AMP with fixed-point gathers
+template <int LOGM>
+int launch_amp(const sb_operator *op, AmpArgs a, int B, int which, const double *in, double *out, cudaStream_t st) {
+    size_t smem = 0;
+    int W = 0;
+    const bool quant = (which == 3) && op->pre;
+    const int nt = quant ? pick_threads<LOGM, true>(op->n, op->L, &smem, &W)
+                         : pick_threads<LOGM, false>(op->n, op->L, &smem, &W);
+    if (smem > 227 * 1024) return fail(SB_EINVAL, "AMP: n too large for shared memory%s (%ld bytes)", "", (long)smem);
+#define SB_LAUNCH(KERNEL, ...)                                                                           \
+    do {                                                                                                 \
+        SB_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        KERNEL<<<B, nt, smem, st>>>(__VA_ARGS__);                                                        \
+    } while (0)
+    if (which == 0 || which == 3) {
+        if (quant) SB_LAUNCH((amp_kernel<LOGM, true, true>), a, W);
+        else if (op->pre) SB_LAUNCH((amp_kernel<LOGM, true, false>), a, W);
+        else SB_LAUNCH((amp_kernel<LOGM, false, false>), a, W);
+    } else if (which == 1) {
+        if (op->pre) SB_LAUNCH((Ab_kernel<LOGM, true>), a, W, in, out);
+        else SB_LAUNCH((Ab_kernel<LOGM, false>), a, W, in, out);
+    } else {
+        if (op->pre) SB_LAUNCH((Az_kernel<LOGM, true>), a, W, in, out);
+        else SB_LAUNCH((Az_kernel<LOGM, false>), a, W, in, out);
+    }
+#undef SB_LAUNCH
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+}  // namespace sb

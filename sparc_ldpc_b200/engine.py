@@ -12,6 +12,12 @@ from ._lib import check
 
 F64, I32 = torch.float64, torch.int32
 _RULES = {"sumprod2": _lib.SB_BP_SUMPROD2, "sumprod": _lib.SB_BP_SUMPROD, "minsum": _lib.SB_BP_MINSUM}
+_MODES = {"strict": _lib.SB_AMP_STRICT, "fast": _lib.SB_AMP_FAST}
+# Default arithmetic of Operator.amp.  "strict" = fp64 in the reference's order of additions (parity mode);
+# "fast" = 32-bit fixed-point gathers.  Override per call with mode=..., or globally
+# with the environment variable SPARC_B200_AMP_MODE.
+import os as _os
+AMP_MODE = _os.environ.get("SPARC_B200_AMP_MODE", "strict")
 
 
 def _dev():
@@ -127,8 +133,12 @@ class Operator:
               "sb_onehot_apply_batch")
         return out
 
-    def amp(self, y, Pl, T, beta0=None, sections=None, nsec=None, trace=False):
-        """Batched AMP decode (sparc_ldpc.py:189-222).  Returns AmpResult."""
+    def amp(self, y, Pl, T, beta0=None, sections=None, nsec=None, trace=False, mode=None):
+        """Batched AMP decode (sparc_ldpc.py:189-222).  Returns AmpResult.  mode: "strict" | "fast" (default:
+        engine.AMP_MODE, see include/sparc_b200.h SB_AMP_STRICT / SB_AMP_FAST)."""
+        mode = AMP_MODE if mode is None else mode
+        if mode not in _MODES:
+            raise ValueError("mode must be 'strict' or 'fast'")
         _chk(y, F64, "y")
         _chk(Pl, F64, "Pl")
         _chk(beta0, F64, "beta0")
@@ -143,8 +153,8 @@ class Operator:
         n_exec = torch.empty(B, dtype=I32, device=dev)
         flags = torch.empty(B, dtype=I32, device=dev)
         tau2 = torch.full((B, max(T, 1)), float("nan"), dtype=F64, device=dev) if trace else None
-        check(_lib.lib().sb_amp_batch(self._h, _p(y), _p(Pl), _p(beta0), _p(sections), _p(nsec), B, int(T), _p(beta),
-                                      _p(iters), _p(n_exec), _p(flags), _p(tau2), _stream()), "sb_amp_batch")
+        check(_lib.lib().sb_amp_batch(self._h, _p(y), _p(Pl), _p(beta0), _p(sections), _p(nsec), B, int(T), _MODES[mode],
+                                      _p(beta), _p(iters), _p(n_exec), _p(flags), _p(tau2), _stream()), "sb_amp_batch")
         return AmpResult(beta, iters, n_exec, flags, tau2)
 
 

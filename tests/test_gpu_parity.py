@@ -111,51 +111,58 @@ def test_operator_linearity_full_size(Eng):
 
 
 # ------------------------------------------------------------------------------------------- AMP
-def _amp_trace(op, y, Pl, T, beta0=None):
+FAST = 2e-6              # "fast" mode (32-bit fixed-point gathers, SB_AMP_FAST): measured ~1e-8, asserted 2e-6
+MODE_TOL = {"strict": TIGHT, "fast": FAST}
+
+
+def _amp_trace(op, y, Pl, T, beta0=None, mode="strict"):
     """beta after each iteration by re-running with T = 1..; returns (betas, last result)."""
     yd, Pld = cu(y.reshape(1, -1)), cu(Pl)
     b0 = None if beta0 is None else cu(beta0.reshape(1, -1))
-    full = op.amp(yd, Pld, T, beta0=b0, trace=True)
+    full = op.amp(yd, Pld, T, beta0=b0, trace=True, mode=mode)
     nex = int(full.n_exec[0])
-    betas = [op.amp(yd, Pld, t, beta0=b0).beta.cpu().numpy().reshape(-1) for t in range(1, nex + 1)]
+    betas = [op.amp(yd, Pld, t, beta0=b0, mode=mode).beta.cpu().numpy().reshape(-1) for t in range(1, nex + 1)]
     return betas, full
 
 
+@pytest.mark.parametrize("mode", ["strict", "fast"])
 @pytest.mark.parametrize("k", [0, 1, "w"])
-def test_amp_trace_c1(Eng, k):
+def test_amp_trace_c1(Eng, k, mode):
     g = golden("amp_small")
     L, M, P, T, n = 128, 4, 2.0, 64, 256
     Pl = P / L * np.ones(L)
     op = Eng.get_operator(L, M, n, 0)
     p = "c1_w_" if k == "w" else "c1_%d_" % k
     y = g["c1_0_y"] if k == "w" else g[p + "y"]
-    betas, full = _amp_trace(op, y, Pl, T, g["c1_w_init"] if k == "w" else None)
+    betas, full = _amp_trace(op, y, Pl, T, g["c1_w_init"] if k == "w" else None, mode)
     assert int(full.iters[0]) == int(g[p + "t"])
     tau2 = full.tau2.cpu().numpy().reshape(-1)[:len(betas)]
     err_t = relinf(tau2, g[p + "tau2"][:len(betas)])
     err_b = max(relinf(b, r) for b, r in zip(betas, g[p + "beta_trace"]))
-    print("C1 %s: max rel err tau2 %.2e, beta %.2e over %d iterations" % (k, err_t, err_b, len(betas)))
+    print("C1 %s [%s]: max rel err tau2 %.2e, beta %.2e over %d iterations" % (k, mode, err_t, err_b, len(betas)))
     assert len(betas) == len(g[p + "beta_trace"])
     assert err_t < NORTH_STAR_RTOL and err_b < NORTH_STAR_RTOL
-    assert err_t < TIGHT and err_b < TIGHT
-    assert relinf(full.beta.cpu().numpy().reshape(-1), g[p + "beta"]) < TIGHT
+    assert err_t < MODE_TOL[mode] and err_b < MODE_TOL[mode]
+    assert relinf(full.beta.cpu().numpy().reshape(-1), g[p + "beta"]) < MODE_TOL[mode]
 
 
-def test_amp_power_allocation(Eng):
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_amp_power_allocation(Eng, mode):
     g = golden("amp_small")
     L, M, T = 32, 64, 64
     n = L * 6
     op = Eng.get_operator(L, M, n, 0)
-    betas, full = _amp_trace(op, g["pa_y"], g["pa_Pl"], T)
+    betas, full = _amp_trace(op, g["pa_y"], g["pa_Pl"], T, mode=mode)
     assert int(full.iters[0]) == int(g["pa_t"])
     err_b = max(relinf(b, r) for b, r in zip(betas, g["pa_beta_trace"]))
     err_t = relinf(full.tau2.cpu().numpy().reshape(-1)[:len(betas)], g["pa_tau2"][:len(betas)])
-    print("PA: max rel err tau2 %.2e beta %.2e" % (err_t, err_b))
-    assert err_b < TIGHT and err_t < TIGHT
+    print("PA [%s]: max rel err tau2 %.2e beta %.2e" % (mode, err_t, err_b))
+    assert err_b < MODE_TOL[mode] and err_t < MODE_TOL[mode]
 
 
+@pytest.mark.parametrize("mode", ["strict", "fast"])
 @pytest.mark.parametrize("k", [0, 1])
-def test_amp_c3_shape(Eng, S, k):
+def test_amp_c3_shape(Eng, S, k, mode):
     """L = M = 512, n = 4608: tau^2 per iteration, per-section argmax / max per iteration, early-stop index."""
     g = golden("amp_c3")
     L, M, n, T = 512, 512, 4608, 64
@@ -163,13 +170,14 @@ def test_amp_c3_shape(Eng, S, k):
     op = Eng.get_operator(L, M, n, 0)
     p = "c3_%d_" % k
     yd, Pld = cu(g[p + "y"].reshape(1, -1)), cu(Pl)
-    full = op.amp(yd, Pld, T, trace=True)
+    full = op.amp(yd, Pld, T, trace=True, mode=mode)
     nex, nref = int(full.n_exec[0]), len(g[p + "tau2"])
     # The exact-equality stop (tau == last_tau, sparc_ldpc.py:204) fires when the fp64 state reaches an exact
     # fixed point; which iteration that is depends on last-ulp rounding (CUDA vs numpy exp), so the index may
     # differ by a few iterations while the state agrees to ~1e-15 (documented near-tie class).
-    assert abs(nex - nref) <= 4, (nex, nref)
-    assert (int(full.iters[0]) < T - 1) == (int(g[p + "t"]) < T - 1)
+    if mode == "strict":
+        assert abs(nex - nref) <= 4, (nex, nref)
+        assert (int(full.iters[0]) < T - 1) == (int(g[p + "t"]) < T - 1)
     nex = min(nex, nref)
     tau2 = full.tau2.cpu().numpy().reshape(-1)[:nex]
     err_t = relinf(tau2, g[p + "tau2"][:nex])
@@ -177,7 +185,7 @@ def test_amp_c3_shape(Eng, S, k):
     for t in (1, 2, 5, 10, nex):
         if t > nex:
             continue
-        r = op.amp(yd, Pld, t)
+        r = op.amp(yd, Pld, t, mode=mode)
         b = r.beta.cpu().numpy().reshape(L, M)
         assert np.array_equal(b.argmax(axis=1), g[p + "argmax_trace"][t - 1])
         worst = max(worst, relinf(b.max(axis=1), g[p + "max_trace"][t - 1]),
@@ -185,9 +193,11 @@ def test_amp_c3_shape(Eng, S, k):
     post = full.beta.cpu().numpy().reshape(-1) / np.sqrt(n * np.repeat(Pl, M))
     bitwise = S.sp2bp(post, L, M)
     err_p = float(np.max(np.abs(bitwise - g[p + "bitwise"])))
-    print("C3 %d: %d iterations, rel err tau2 %.2e, section max %.2e, |d bitwise| %.2e" % (k, nex, err_t, worst, err_p))
+    print("C3 %d [%s]: %d iterations (ref %d), rel err tau2 %.2e, section max %.2e, |d bitwise| %.2e"
+          % (k, mode, int(full.n_exec[0]), nref, err_t, worst, err_p))
     assert err_t < NORTH_STAR_RTOL and worst < NORTH_STAR_RTOL
-    assert err_t < 1e-8 and worst < 1e-8 and err_p < 1e-8
+    tol = 1e-8 if mode == "strict" else FAST
+    assert err_t < tol and worst < tol and err_p < tol
 
 
 def test_amp_batch_consistency_and_edge_cases(Eng):
@@ -371,6 +381,33 @@ def test_link_sims_against_reference(S, case):
     assert chaotic.sum() <= 1
 
 
+@pytest.mark.parametrize("case", FLOW_CASES, ids=[c[0] for c in FLOW_CASES])
+def test_link_sims_fast_mode(S, Eng, case, monkeypatch):
+    """The same flows with the fixed-point gathers (SB_AMP_FAST): decisions and BER counts must not move
+    (they are quantised far above the 1e-8 perturbation), except on chaotic BP blocks."""
+    tag, fn, spk, lpk, kw, reps = case
+    monkeypatch.setattr(Eng, "AMP_MODE", "fast")
+    g = golden("flows_small")
+    np.random.seed(int(g[tag + "_seed"]))
+    sp = S.SPARCParams(**spk)
+    lp = None if lpk is None else S.LDPCParams(*lpk)
+    rows = []
+    for _ in range(reps):
+        if fn == "amp_ldpc_sim":
+            res = S.amp_ldpc_sim(sp, lp)
+        elif fn == "soft_amp_ldpc_sim":
+            res = S.soft_amp_ldpc_sim(sp, lp, kw["soft_iter"])
+        elif fn == "hardinitbeta_amp_ldpc_sim":
+            res = S.hardinitbeta_amp_ldpc_sim(sp, lp)
+        else:
+            res = S.soft_amp_ldpc_hardinit(sp, lp, kw["soft_iter"], kw["threshold"])
+        rows.append(flat_result(res))
+    rows, ref = np.array(rows), g[tag + "_res"]
+    chaotic = (g[tag + "_its"] >= 200).any(axis=1) if g[tag + "_its"].size else np.zeros(reps, dtype=bool)
+    np.testing.assert_array_equal(rows[~chaotic], ref[~chaotic])
+    np.testing.assert_array_equal(rows[chaotic][:, 0], ref[chaotic][:, 0])
+
+
 def test_batch_equals_sequential(S):
     """B codewords in one pass == B single-codeword calls on the same RNG stream."""
     sp = S.SPARCParams(L=64, M=8, sigma=0.8, p=4, r=1, t=64)
@@ -383,9 +420,11 @@ def test_batch_equals_sequential(S):
         assert a1 == ba[b].tolist() and l1 == bl[b].tolist() and R1 == R
 
 
+@pytest.mark.parametrize("mode", ["strict", "fast"])
 @pytest.mark.parametrize("tag", ["soft", "hard", "thr"])
-def test_c3_flows_against_reference(S, tag):
+def test_c3_flows_against_reference(S, Eng, tag, mode, monkeypatch):
     """One full-size codeword per flow: L = M = 512, 802.16 rate 5/6 z = 192 (BASELINE configs[2])."""
+    monkeypatch.setattr(Eng, "AMP_MODE", mode)
     g = golden("flows_c3")
     np.random.seed(int(g[tag + "_seed"]))
     sp = S.SPARCParams(L=512, M=512, sigma=float(g[tag + "_sigma"]), p=4, r=1, t=64)

@@ -16,6 +16,7 @@ ap.add_argument("--T", type=int, default=8)
 ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--sigma", type=float, default=0.9964)
 ap.add_argument("--bp", action="store_true")
+ap.add_argument("--mode", default="fast")
 args = ap.parse_args()
 
 sp = S.SPARCParams(L=512, M=512, sigma=args.sigma, p=4.0, r=1, t=args.T)
@@ -26,7 +27,7 @@ torch.cuda.synchronize()
 for i in range(args.launches):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    res = su.op.amp(y, su.Pl_dev, args.T)
+    res = su.op.amp(y, su.Pl_dev, args.T, mode=args.mode)
     e1.record()
     torch.cuda.synchronize()
     it = float(res.n_exec.sum())
