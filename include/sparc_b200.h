@@ -108,7 +108,9 @@ int sb_onehot_apply_batch(const sb_operator *op, const int *idx, const double *P
 #define SB_AMP_STRICT 0 /* fp64 everywhere, reference order of additions: A beta / A^T z bit-identical           */
 #define SB_AMP_FAST 1   /* z and FHT(beta) are gathered from 32-bit fixed-point copies (27 bits below their
                            power-of-two ceiling), adds of the two gathers are exact integer adds; FHT, softmax,
-                           z update and tau^2 stay fp64.  beta / tau^2 agree with STRICT to ~1e-8 relative.    */
+                           z update and tau^2 stay fp64.  beta / tau^2 agree with STRICT to ~1e-8 relative.  The
+                           stop rule becomes |tau - last_tau| <= 2^-27 tau (tau cannot reach an exact fixed point
+                           above the quantisation floor), so `iters` is smaller than in STRICT mode.                */
 int sb_amp_batch(const sb_operator *op, const double *y, const double *Pl, const double *beta0, const int *sections,
                  const int *nsec, int B, int T, int mode, double *beta, int *iters, int *n_exec, unsigned *flags,
                  double *tau2_trace, void *stream);

@@ -302,51 +302,74 @@ __device__ __forceinline__ void gather_phase(const uint16_t *__restrict__ fwd, i
 }
 
 // all sections in order and groups aligned to 8: the 8 entries of (group, k) are one 16-byte load from the
-// interleaved table.  KB rows per thread are in flight together and chunk c+1 is loaded while chunk c is used.
+// interleaved table.  KB rows per thread are in flight together.  Full pairs of chunks (16 sections, the
+// headline group size) take a predicate-free path; a trailing chunk takes the guarded one.
+template <int LOGM, typename T, int KB>
+__device__ __forceinline__ void gather_chunk(const uint4 (&w)[KB], const char *F, int nv, double (&acc)[KB],
+                                             T (&part)[KB]) {
+    constexpr int ESH = sizeof(T) == 8 ? 3 : 2;
+#pragma unroll
+    for (int j = 0; j < KB; j++) {
+        const uint32_t wds[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (nv >= 8 || i < nv) {
+                const uint32_t e = (i & 1) ? (wds[i >> 1] >> 16) : (wds[i >> 1] & 0xFFFFu);
+                const T v = F_at<T>(F + slot_offset<LOGM, ESH>(i), e);
+                if (sizeof(T) == 8) acc[j] += v; else part[j] += v;
+            }
+        }
+    }
+}
+
 template <int LOGM, typename T>
 __device__ __forceinline__ void gather_phase8(const uint16_t *__restrict__ fwd8, int n, int g0, int nvalid,
                                               const char *Fbytes, double *acc_s, double funit) {
-    constexpr int KB = 4;
+    constexpr int KB = 3;
     constexpr int ESH = sizeof(T) == 8 ? 3 : 2;
     const uint4 *tab = reinterpret_cast<const uint4 *>(fwd8) + (size_t)(g0 >> 3) * n;
-    const int nch = (nvalid + 7) >> 3, NT = blockDim.x;
+    const int nfull = nvalid >> 3, NT = blockDim.x;  // complete chunks of 8 sections
     for (int k0 = threadIdx.x; k0 < n; k0 += KB * NT) {
         double acc[KB];
         T part[KB];
-        uint4 w[KB];
+        int kk[KB];
 #pragma unroll
         for (int j = 0; j < KB; j++) {
             const int k = k0 + j * NT;
-            acc[j] = (k < n) ? acc_s[k] : 0.0;
+            kk[j] = (k < n) ? k : k0;  // clamp: a duplicate row is gathered and then discarded
+            acc[j] = acc_s[kk[j]];
             part[j] = 0;
-            w[j] = (k < n) ? __ldg(tab + k) : make_uint4(0, 0, 0, 0);
         }
-        for (int c = 0; c < nch; c++) {
-            uint4 wn[KB];
+        int c = 0;
+        for (; c + 2 <= nfull; c += 2) {  // 16 sections: two 16-byte loads per row, no predicates
+            uint4 w0[KB], w1[KB];
 #pragma unroll
             for (int j = 0; j < KB; j++) {
-                const int k = k0 + j * NT;
-                wn[j] = (c + 1 < nch && k < n) ? __ldg(tab + (size_t)(c + 1) * n + k) : make_uint4(0, 0, 0, 0);
+                w0[j] = __ldg(tab + (size_t)c * n + kk[j]);
+                w1[j] = __ldg(tab + (size_t)(c + 1) * n + kk[j]);
             }
-            const char *F = Fbytes + slot_offset<LOGM, ESH>(c * 8);  // c*8 is a multiple of SPR: region start
-            const bool full = (c * 8 + 8 <= nvalid);
-            const bool flush = (sizeof(T) != 8) && ((c & 1) == 1 || c + 1 == nch);  // <= 16 int32 terms per flush
+            const char *F = Fbytes + slot_offset<LOGM, ESH>(c * 8);
+            gather_chunk<LOGM, T, KB>(w0, F, 8, acc, part);
+            gather_chunk<LOGM, T, KB>(w1, F + slot_offset<LOGM, ESH>(8), 8, acc, part);
+            if (sizeof(T) != 8) {  // <= 16 int32 terms of < 2^27 each per flush
 #pragma unroll
-            for (int j = 0; j < KB; j++) {
-                const uint32_t wds[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (full || c * 8 + i < nvalid) {
-                        const uint32_t e = (i & 1) ? (wds[i >> 1] >> 16) : (wds[i >> 1] & 0xFFFFu);
-                        const T v = F_at<T>(F + slot_offset<LOGM, ESH>(i), e);
-                        if (sizeof(T) == 8) acc[j] += v; else part[j] += v;
-                    }
-                }
-                if (flush) {
+                for (int j = 0; j < KB; j++) {
                     acc[j] += (double)part[j] * funit;
                     part[j] = 0;
                 }
-                w[j] = wn[j];
+            }
+        }
+        for (; c * 8 < nvalid; c++) {  // trailing chunk(s), possibly partial
+            uint4 w0[KB];
+#pragma unroll
+            for (int j = 0; j < KB; j++) w0[j] = __ldg(tab + (size_t)c * n + kk[j]);
+            gather_chunk<LOGM, T, KB>(w0, Fbytes + slot_offset<LOGM, ESH>(c * 8), nvalid - c * 8, acc, part);
+            if (sizeof(T) != 8) {
+#pragma unroll
+                for (int j = 0; j < KB; j++) {
+                    acc[j] += (double)part[j] * funit;
+                    part[j] = 0;
+                }
             }
         }
 #pragma unroll
@@ -498,7 +521,10 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
             zmax = fmax(zmax, fabs(zf[k]));
         }
         const double tau = sqrt(block_sum(part, red) / nd);  // (:203)
-        if (tau == last_tau) {                               // exact-equality stop (:204)
+        // exact-equality stop (:204).  With fixed-point gathers tau jitters at the quantisation floor instead
+        // of reaching an exact fp64 fixed point, so FAST mode stops once tau moves by less than 2^-27 relative:
+        // beta is then within ~1e-8 of the fixed point the reference iterates on to.
+        if (tau == last_tau || (QUANT && fabs(tau - last_tau) <= tau * 7.450580596923828e-09)) {
             flags |= SB_AMP_STOPPED;
             break;
         }

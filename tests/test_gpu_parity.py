@@ -135,12 +135,15 @@ def test_amp_trace_c1(Eng, k, mode):
     p = "c1_w_" if k == "w" else "c1_%d_" % k
     y = g["c1_0_y"] if k == "w" else g[p + "y"]
     betas, full = _amp_trace(op, y, Pl, T, g["c1_w_init"] if k == "w" else None, mode)
-    assert int(full.iters[0]) == int(g[p + "t"])
+    if mode == "strict":
+        assert int(full.iters[0]) == int(g[p + "t"])
+    else:  # FAST stops at |d tau| <= 2^-27 tau: never later than the reference's exact-equality stop
+        assert int(full.iters[0]) <= int(g[p + "t"])
     tau2 = full.tau2.cpu().numpy().reshape(-1)[:len(betas)]
     err_t = relinf(tau2, g[p + "tau2"][:len(betas)])
     err_b = max(relinf(b, r) for b, r in zip(betas, g[p + "beta_trace"]))
     print("C1 %s [%s]: max rel err tau2 %.2e, beta %.2e over %d iterations" % (k, mode, err_t, err_b, len(betas)))
-    assert len(betas) == len(g[p + "beta_trace"])
+    assert len(betas) == len(g[p + "beta_trace"]) or mode == "fast"
     assert err_t < NORTH_STAR_RTOL and err_b < NORTH_STAR_RTOL
     assert err_t < MODE_TOL[mode] and err_b < MODE_TOL[mode]
     assert relinf(full.beta.cpu().numpy().reshape(-1), g[p + "beta"]) < MODE_TOL[mode]
@@ -153,7 +156,7 @@ def test_amp_power_allocation(Eng, mode):
     n = L * 6
     op = Eng.get_operator(L, M, n, 0)
     betas, full = _amp_trace(op, g["pa_y"], g["pa_Pl"], T, mode=mode)
-    assert int(full.iters[0]) == int(g["pa_t"])
+    assert int(full.iters[0]) == int(g["pa_t"]) or (mode == "fast" and int(full.iters[0]) <= int(g["pa_t"]))
     err_b = max(relinf(b, r) for b, r in zip(betas, g["pa_beta_trace"]))
     err_t = relinf(full.tau2.cpu().numpy().reshape(-1)[:len(betas)], g["pa_tau2"][:len(betas)])
     print("PA [%s]: max rel err tau2 %.2e beta %.2e" % (mode, err_t, err_b))
@@ -406,6 +409,33 @@ def test_link_sims_fast_mode(S, Eng, case, monkeypatch):
     chaotic = (g[tag + "_its"] >= 200).any(axis=1) if g[tag + "_its"].size else np.zeros(reps, dtype=bool)
     np.testing.assert_array_equal(rows[~chaotic], ref[~chaotic])
     np.testing.assert_array_equal(rows[chaotic][:, 0], ref[chaotic][:, 0])
+
+
+def test_fast_mode_decisions_equal_strict_on_converged_codewords(S, Eng):
+    """Bench operating point (L = M = 512, sigma = 0.9964, soft exchange): every codeword whose AMP decodes all
+    converge (early stop) must give identical decisions at every stage in STRICT and FAST mode; codewords that
+    never converge (64 iterations) are chaotic and may differ."""
+    from sparc_ldpc_b200 import decoder as D
+    sp = S.SPARCParams(L=512, M=512, sigma=0.9963928922771221, p=4.0, r=1, t=64)
+    su = D.make_setup(sp, S.LDPCParams("802.16", "5/6", 192))
+    idx, noise = S._draw(su, 48, sp.sigma, np.random.RandomState(3))
+    tx, y = S._transmit(su, idx, noise)
+    out = {}
+    for mode in ("strict", "fast"):
+        Eng.AMP_MODE = mode
+        try:
+            st = D.soft(su, y, 2)
+        finally:
+            Eng.AMP_MODE = "strict"
+        out[mode] = ([a.cpu().numpy() for a in st.amp_idx], [a.cpu().numpy() for a in st.ldpc_idx],
+                     np.stack([e.cpu().numpy() for e in st.amp_exec]), np.stack([b.cpu().numpy() for b in st.bp_it]))
+    conv = (out["strict"][2] < 64).all(axis=0) & (out["strict"][3] < 200).all(axis=0)
+    print("converged codewords: %d of %d; mean AMP iterations strict %.1f fast %.1f"
+          % (conv.sum(), conv.size, out["strict"][2].mean(), out["fast"][2].mean()))
+    assert conv.sum() >= 24
+    for a, b in zip(out["strict"][0] + out["strict"][1], out["fast"][0] + out["fast"][1]):
+        assert np.array_equal(a[conv], b[conv])
+    assert (out["fast"][2] <= out["strict"][2]).all()
 
 
 def test_batch_equals_sequential(S):
