@@ -85,6 +85,9 @@ typedef struct sb_operator sb_operator;
 int sb_operator_create(const uint32_t *ordering_host, int L, int M, int n, sb_operator **out);
 void sb_operator_destroy(sb_operator *op);
 
+/* pyfht.fht_inplace (sparc_ldpc.py:14-29, :69, :76): HOST pointer, N a power of two, transformed in place. */
+int sb_fht_inplace_host(double *x, long N);
+
 /* out[b][0..n) = A_S beta[b] where S = the codeword's section list (sparc_ldpc.py:143-144;
  * sparc_transforms_shorter :154-168 when `sections` is given).  beta[b] is compact:
  * nsec[b]*M entries.  sections == NULL: all L sections in order; nsec == NULL: L. */

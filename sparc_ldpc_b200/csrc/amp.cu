@@ -35,6 +35,16 @@ __global__ void onehot_kernel(const uint16_t *__restrict__ fwd, int L, int n, in
     out[(size_t)b * n + k] = (sign < 0) ? (base - x) : (base + x);
 }
 
+// one butterfly stage of the in-place Walsh-Hadamard transform (ldpc/sparc_ldpc.py:19-29): stride h
+__global__ void fht_stage_kernel(double *x, long N, long h) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N / 2) return;
+    const long j = (t / h) * 2 * h + (t % h);
+    const double a = x[j], b = x[j + h];
+    x[j] = a + b;
+    x[j + h] = a - b;
+}
+
 extern template int launch_amp<1>(const sb_operator *, AmpArgs, int, int, const double *, double *, cudaStream_t);
 extern template int launch_amp<2>(const sb_operator *, AmpArgs, int, int, const double *, double *, cudaStream_t);
 extern template int launch_amp<3>(const sb_operator *, AmpArgs, int, int, const double *, double *, cudaStream_t);
@@ -156,6 +166,25 @@ extern "C" int sb_Az_batch(const sb_operator *op, const double *z, const int *se
     if (B == 0) return SB_OK;
     AmpArgs a = base_args(op, sections, nsec);
     return dispatch(op, a, B, 2, z, out, (cudaStream_t)stream);
+}
+
+// pyfht.fht_inplace replacement (sparc_ldpc.py:14-29): host pointer, length a power of two, transformed in place
+// with the stages in the reference's order (strides N/2 ... 1), hence bit-identical to it.
+extern "C" int sb_fht_inplace_host(double *x, long N) {
+    if (!x || N <= 0 || (N & (N - 1))) return fail(SB_EINVAL, "sb_fht_inplace_host: length must be a power of two%s (%ld)", "", N);
+    if (N == 1) return SB_OK;
+    double *d = nullptr;
+    SB_CUDA(cudaMalloc(&d, sizeof(double) * N));
+    cudaError_t e = cudaMemcpy(d, x, sizeof(double) * N, cudaMemcpyHostToDevice);
+    for (long h = N >> 1; h && e == cudaSuccess; h >>= 1) {
+        fht_stage_kernel<<<(unsigned)((N / 2 + 255) / 256), 256>>>(d, N, h);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(x, d, sizeof(double) * N, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(SB_ECUDA, "sb_fht_inplace_host: %s", cudaGetErrorString(e));
+    return SB_OK;
 }
 
 extern "C" int sb_onehot_apply_batch(const sb_operator *op, const int *idx, const double *Pl, const double *y,

@@ -47,9 +47,12 @@ def pa_parameterised(L, C, P, a, f):
 
 # ----------------------------------------------------------------------------------- operators
 def fht_inplace(x):
-    """API-completeness shim for pyfht.fht_inplace (sparc_ldpc.py:14-29): a length-w Hadamard transform is
-    the M = w, L = 1, n = w-1 instance of the device operator's transform; not on any hot path."""
-    raise NotImplementedError("fht_inplace is superseded by the operator-level boundary (sparc_transforms)")
+    """pyfht.fht_inplace (sparc_ldpc.py:14-29): in-place unnormalised Walsh-Hadamard transform of a 1-D
+    C-contiguous float64 array whose length is a power of two; same butterfly order, hence bit-identical."""
+    if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous and x.ndim == 1):
+        raise TypeError("fht_inplace needs a 1-D C-contiguous float64 array")
+    from . import _lib
+    _lib.check(_lib.lib().sb_fht_inplace_host(x.ctypes.data, x.size), "sb_fht_inplace_host")
 
 
 def _to_dev(a, cols):

@@ -1,0 +1,188 @@
+"""GPU tests of the reference-facing drivers (stop-rule replay, RNG draw order, CSV schema) and of the small
+API-completeness entry points.  The expected values are produced by replaying the reference's driver loops
+(ldpc/sparc_ldpc.py:1183-1251, ldpc/amp_exit.py:560-595) with the CPU oracle's per-codeword functions on the
+same legacy numpy stream; equality of the RNG state after the call proves that exactly the same draws were
+consumed."""
+import csv
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def same_state(a, b):
+    return a[0] == b[0] and np.array_equal(a[1], b[1]) and a[2:] == b[2:]
+
+
+def test_fht_inplace_bit_exact(oracle):
+    from sparc_ldpc_b200 import sparc_ldpc as S
+    rs = np.random.RandomState(0)
+    for N in (2, 8, 512, 8192):
+        x = rs.randn(N)
+        ref = x.copy()
+        oracle.fht_inplace(ref)
+        S.fht_inplace(x)
+        assert np.array_equal(x, ref)
+    with pytest.raises(Exception):
+        S.fht_inplace(np.zeros(12))
+
+
+def test_hard_initialisation_facade(oracle):
+    from sparc_ldpc_b200 import amp_exit as AE, sparc_ldpc as S
+    L, M, n = 24, 8, 72
+    rs = np.random.RandomState(3)
+    Pl = 4.0 / L * np.ones(L)
+    post = rs.dirichlet(np.ones(M) * 0.1, size=L).reshape(-1)
+    y = rs.randn(n, 1)
+    Ab, Az, ordering = S.sparc_transforms(L, M, n)
+    Abo, Azo, ordo = oracle.sparc_transforms(L, M, n)
+    b1, b2 = post.copy(), post.copy()
+    y1, Ab1, Az1, sec1, La1 = AE.hard_initialisation(b1, L, M, n, ordering, y, Pl, Ab, 0.6, 16)
+    y2, Ab2, Az2, sec2, La2 = oracle.hard_initialisation(b2, L, M, n, ordo, y, Pl, Abo, 0.6, 16)
+    assert sec1 == sec2 and La1 == La2 and 0 < La1 < L
+    assert np.array_equal(b1, b2)            # the input is overwritten exactly like the reference does
+    assert np.array_equal(y1, y2)
+    v = rs.randn(La1 * M)
+    assert np.array_equal(Ab1(v), Ab2(v))
+    assert np.array_equal(Az1(y), Az2(y))
+
+
+def test_sim_ldpc_stop_rule_and_rng(oracle):
+    from sparc_ldpc_b200 import sparc_ldpc as S
+    lp = ("802.16", "5/6", 8)
+    sigma = 0.62
+    r1, r2 = np.random.RandomState(11), np.random.RandomState(11)
+    ber_ref = oracle.sim_ldpc(oracle.LDPCParams(*lp), sigma, MIN_ERRORS=4, MAX_BLOCKS=60, rng=r2)
+    ber = S.sim_ldpc(S.LDPCParams(*lp), sigma, MIN_ERRORS=4, MAX_BLOCKS=60, chunk=16, rng=r1)
+    assert same_state(r1.get_state(), r2.get_state())     # same number of blocks drawn, RNG rewound correctly
+    assert ber_ref > 0 and abs(ber - ber_ref) <= 0.35 * ber_ref  # error blocks are non-convergent (chaotic counts)
+    # MAX_BLOCKS cut with no errors at all
+    r1, r2 = np.random.RandomState(12), np.random.RandomState(12)
+    assert S.sim_ldpc(S.LDPCParams(*lp), 0.3, 2, 5, chunk=3, rng=r1) == oracle.sim_ldpc(oracle.LDPCParams(*lp), 0.3, 2, 5, rng=r2) == 0.0
+    assert same_state(r1.get_state(), r2.get_state())
+    with pytest.raises(NameError):
+        S.sim_ldpc(S.LDPCParams("802.16", "7/8", 8), 0.5)
+
+
+def _waterfall_reference(orc, L, M, p, r, T, sections, grid, MIN_ERRORS, MAX_BLOCKS, rng, init="soft"):
+    """The loop of sparc_ldpc.py:1183-1251 replayed with oracle functions."""
+    logm = np.log2(M)
+    nl = logm * sections
+    z = int(nl / 24)
+    lp = orc.LDPCParams("802.16", "5/6", z)
+    n = L * logm / r
+    R = (L * logm - nl * (1 - 5 / 6)) / n
+    out = {k: [] for k in ("amp1", "amp2", "ldpc1", "ldpc2", "plain", "bpsk", "nblocks")}
+    for ebno_db in grid:
+        ebno = 10 ** (ebno_db / 20)
+        out["bpsk"].append(orc.sim_ldpc(lp, np.sqrt((1 / ebno) / 2), MIN_ERRORS, MAX_BLOCKS, rng=rng))
+        sigma = np.sqrt(p / (ebno / (1 / (2 * R))))
+        sp_c = orc.SPARCParams(L, M, sigma, p, r, T)
+        sp_p = orc.SPARCParams(L, M, sigma, p, R, T)
+        acc = np.zeros(5)
+        nerr = nblocks = 0
+        while nerr < MIN_ERRORS:
+            if init == "soft":
+                ba, bl, _ = orc.soft_amp_ldpc_sim(sp_c, lp, 2, rng=rng)
+            else:
+                ba, bl, _ = orc.hardinitbeta_amp_ldpc_sim(sp_c, lp, rng=rng)
+                bl = bl + [0]
+            bp, _, _, _ = orc.amp_ldpc_sim(sp_p, rng=rng)
+            acc += [ba[0], ba[1], bl[0], bl[1], bp]
+            nerr += 1 if bp else 0
+            nblocks += 1
+            if nblocks >= MAX_BLOCKS:
+                break
+        for k, v in zip(("amp1", "amp2", "ldpc1", "ldpc2", "plain"), acc / nblocks):
+            out[k].append(v)
+        out["nblocks"].append(nblocks)
+    return out
+
+
+@pytest.mark.parametrize("init", ["soft", "hard"])
+def test_waterfall_driver(oracle, tmp_path, init):
+    from sparc_ldpc_b200 import sparc_ldpc as S
+    L, M, p, r, T = 64, 8, 4.0, 1, 64
+    grid = [6.0, 8.5]
+    r1, r2 = np.random.RandomState(21), np.random.RandomState(21)
+    ref = _waterfall_reference(oracle, L, M, p, r, T, 64, grid, 2, 5, r2, init)
+    csvf = str(tmp_path / "w.csv")
+    cols = S.waterfall(S.SPARCParams(L, M, None, p, r, T), S.LDPCParams("802.16", "5/6", None), csvf, "w.png",
+                       init=init, datapoints=2, MIN_ERRORS=2, MAX_BLOCKS=5, sections=64, chunk=3, EbN0_dB=grid, rng=r1)
+    assert same_state(r1.get_state(), r2.get_state())
+    np.testing.assert_array_equal(cols["BER_plain"], ref["plain"])
+    np.testing.assert_array_equal(cols["BER_amp_1"], ref["amp1"])
+    # stages after an LDPC decode can differ on chaotic (non-convergent) BP blocks only
+    np.testing.assert_allclose(cols["BER_ldpc"], ref["ldpc1"], rtol=0.3, atol=2e-3)
+    np.testing.assert_allclose(cols["BER_amp_2"], ref["amp2"], rtol=0.3, atol=2e-3)
+    rows = list(csv.DictReader(open(csvf)))
+    assert list(rows[0].keys()) == ["EbN0_dB", "BER_amp_1", "BER_ldpc", "BER_amp_2", "BER_ldpc_2", "BER_plain", "BER_bpsk"]
+    assert len(rows) == 2 and float(rows[1]["EbN0_dB"]) == 8.5
+    with pytest.raises(ValueError):
+        S.waterfall(S.SPARCParams(L, M, None, p, r, T), S.LDPCParams("802.16", "5/6", None), csvf, "w.png", init="nope",
+                    sections=64, EbN0_dB=grid)
+
+
+def test_threshold_and_soft_hard_sweeps_write_reference_schema(tmp_path):
+    from sparc_ldpc_b200 import sparc_ldpc as S
+    sp = S.SPARCParams(L=64, M=8, sigma=None, p=4.0, r=1, t=64)
+    f1 = str(tmp_path / "t.csv")
+    out = S.soft_hardinit_plot(sp, S.LDPCParams("802.16", "5/6", None), f1, "t.png", sections=64, datapoints=2, MIN_ERRORS=2,
+                               MAX_BLOCKS=4, soft_iter=2, threshold=0.6, chunk=2, SIGMA=[0.6, 0.9],
+                               rng=np.random.RandomState(5))
+    assert out["BER_amp"].shape == (2, 2) and out["BER_ldpc"].shape == (2, 2)
+    assert out["BER_plain"][0] <= out["BER_plain"][1]
+    assert open(f1).readline().strip() == "EbN0_dB,BER_amp,BER_ldpc,BER_plain"
+    f2 = str(tmp_path / "s.csv")
+    out = S.soft_hard_plot(True, True, 32, 2, sp, S.LDPCParams("802.16", "5/6", None), f2, "s.png", datapoints=2, MIN_ERRORS=2,
+                           MAX_BLOCKS=3, chunk=2, SIGMA=[0.8, 0.5], rng=np.random.RandomState(6))
+    assert out["BER_amp_soft"].shape == (2, 3) and out["BER_amp_hard"].shape == (2, 2)
+    lines = open(f2).read().splitlines()
+    assert lines[0] == "EbN0_dB,BER_sparc,BER_ldpc_soft,BER_amp_soft" and "EbN0_dB,BER_sparc,BER_ldpc_hard,BER_amp_hard" in lines
+
+
+def test_amp_exit_curve_against_oracle(oracle):
+    """amp_exit_curve (amp_exit.py:520-597): nested (repeat, snr, I_a) order, per-repetition I_e averaging."""
+    from sparc_ldpc_b200 import amp_exit as AE, sparc_ldpc as S
+    L, M = 64, 8
+    repeats, xpts, bins, thr = 2, 3, 40, 0.7
+    r1, r2 = np.random.RandomState(31), np.random.RandomState(31)
+    Ia, Ie, poly = AE.amp_exit_curve(S.SPARCParams(L, M, None, 4.0, 1, 64), 10, 13, repeats, xpts, thr, bin_number=bins,
+                                     chunk=7, rng=r1)
+    spo = oracle.SPARCParams(L, M, None, 4.0, 1, 64)
+    acc = np.zeros((4, xpts))
+    for k in range(repeats):
+        for j, s_dB in enumerate(np.linspace(10, 13, 4)):
+            for i, I_a in enumerate(np.linspace(0, 0.99, xpts)):
+                X = oracle.gen_bits(L * 3, r2)
+                Eo = oracle.calc_E(X, I_a, s_dB, spo, threshold=thr, rng=r2)
+                h = oracle.hist_E(X, Eo, bins, 60, -60)
+                acc[j, i] += oracle.calc_I_e(h[0], h[1], h[6])
+    assert same_state(r1.get_state(), r2.get_state())
+    np.testing.assert_allclose(Ie, acc / repeats, rtol=1e-9, atol=1e-12)
+    assert poly.shape == (4,) and np.array_equal(Ia, np.linspace(0, 0.99, xpts))
+
+
+def test_exit_chart_closed_forms():
+    from sparc_ldpc_b200 import EXIT_chart as X, amp_exit as AE
+    assert abs(AE.J(AE.J_inverse(0.5)) - 0.5) < 5e-3
+    assert 0 < X.I_E_VND(0.3, 3, 10 ** (7 / 20), 5 / 6) < 1
+    assert abs(X.I_A_CND(0.4, 20) - (1 - AE.J(X.J_inverse(0.6) / np.sqrt(19)))) < 1e-15
+    assert abs(X.I_E_REP(0.2, 7) - AE.J(np.sqrt(6) * X.J_inverse(0.8))) < 1e-15
+    v = X.I_E_VND_amp_array(np.array([0.1, 0.5]), np.array([0, 0, 0.8, 0, 0.2]), np.array([0, 0, 0.6, 0, 0.4]),
+                            np.array([0.54, -0.32, 0.59, 0.23]))
+    assert v.shape == (2,) and 0 < v[0] < v[1] < 1
+
+
+def test_errors_mirror_the_reference():
+    from sparc_ldpc_b200 import sparc_ldpc as S
+    Ab, Az, _ = S.sparc_transforms(8, 16, 24)
+    with pytest.raises(AssertionError):
+        Ab(np.zeros(5))
+    with pytest.raises(NotImplementedError):
+        S.amp(np.zeros((24, 1)), None, np.ones(8), 8, 16, 4, lambda b: b, lambda z: z)
+    with pytest.raises(AssertionError):          # LDPC must cover whole sections (sparc_ldpc.py:416)
+        S.soft_amp_ldpc_sim(S.SPARCParams(64, 32, 0.5, 4.0, 1, 8), S.LDPCParams("802.16", "5/6", 8), 1)
