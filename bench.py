@@ -186,21 +186,39 @@ def gpu_arm(args):
         amp_meta.append(r.n_exec)
         return r
 
+    # The batch is cut into `--streams` slices, each decoded on its own CUDA stream: a slice's dependent chain
+    # (AMP -> BP -> AMP ...) is sequential, but the tail of one slice's launch (codewords that run all 64 AMP /
+    # 200 BP iterations) overlaps with the next slice's work instead of idling the other SMs.
+    S_ = max(1, min(args.streams, B))
+    bounds = [(i * B) // S_ for i in range(S_ + 1)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(S_)]
+    tx_sl = [tx[bounds[i]:bounds[i + 1]].contiguous() for i in range(S_)]
+
     def step_device(y):
-        st = D.soft(su, y, SOFT_ITER)
-        stages = [st.amp_idx[0]]
-        for i in range(SOFT_ITER):
-            stages += [st.ldpc_idx[i], st.amp_idx[i + 1]]
-        errs = torch.stack([E.count_errors(s, tx) for s in stages])          # [5, B] bit errors per stage
+        main = torch.cuda.current_stream()
+        outs = []
+        for i, st_ in enumerate(streams):
+            st_.wait_stream(main)
+            with torch.cuda.stream(st_):
+                ys = y[bounds[i]:bounds[i + 1]]
+                st = D.soft(su, ys, SOFT_ITER)
+                stages = [st.amp_idx[0]]
+                for j in range(SOFT_ITER):
+                    stages += [st.ldpc_idx[j], st.amp_idx[j + 1]]
+                errs = torch.stack([E.count_errors(s, tx_sl[i]) for s in stages])      # [5, b] bit errors per stage
+                outs.append((st, errs))
+        for st_ in streams:
+            main.wait_stream(st_)
+        errs = torch.cat([o[1] for o in outs], dim=1)
         totals = errs.sum(dim=1, dtype=torch.int64)
         if world > 1:
             dist.all_reduce(totals)                                           # the path's only collective
-        return st, errs, totals
+        return [o[0] for o in outs], errs, totals
 
     def step_e2e():
         y = y_host.to(dev, non_blocking=True)
-        st, errs, totals = step_device(y)
-        idx_host.copy_(st.ldpc_idx[-1], non_blocking=True)                   # final decisions
+        sts, errs, totals = step_device(y)
+        idx_host.copy_(torch.cat([s.ldpc_idx[-1] for s in sts]), non_blocking=True)   # final decisions
         errs_host.copy_(errs, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return totals
@@ -226,17 +244,47 @@ def gpu_arm(args):
     bp_its, last = [], None
     for _ in range(args.steps):
         last = step_device(y_dev)
-        bp_its.append(last[0].bp_it)
+        for st in last[0]:
+            bp_its.append(st.bp_it)
     ev1.record()
     barrier()
     launches = _lib.launch_count() - launches0
     ms = ev0.elapsed_time(ev1)
     su.op.amp = orig_amp
-    amp_ms = sum(a.elapsed_time(b) for a, b in amp_events)
+    # time during which at least one amp_kernel launch was executing: union of the per-launch [start, end]
+    # intervals (launches of different streams overlap), from CUDA events on the launching streams
+    iv = sorted((ev0.elapsed_time(a), ev0.elapsed_time(b)) for a, b in amp_events)
+    amp_ms, cur_s, cur_e = 0.0, None, None
+    for s_, e_ in iv:
+        if cur_e is None or s_ > cur_e:
+            if cur_e is not None:
+                amp_ms += cur_e - cur_s
+            cur_s, cur_e = s_, e_
+        else:
+            cur_e = max(cur_e, e_)
+    if cur_e is not None:
+        amp_ms += cur_e - cur_s
     n_amp_launch = len(amp_events)
     exec_iters = float(sum(int(m.sum()) for m in amp_meta))
     bp_iters = float(sum(int(t.sum()) for its in bp_its for t in its))
     amp_events.clear()
+
+    # ---- untimed extra step on ONE stream: the amp kernel's share of a serialised step (what an ncu launch
+    # list of this command shows; with several streams the kernel is busy during ~100 % of the step)
+    su.op.amp = timed_amp
+    streams_saved, bounds_saved, tx_saved = streams, bounds, tx_sl
+    streams, bounds, tx_sl = streams[:1], [0, B], [tx]
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s0.record()
+    step_device(y_dev)
+    s1.record()
+    barrier()
+    share_serial = sum(a.elapsed_time(b) for a, b in amp_events) / s0.elapsed_time(s1)
+    amp_events.clear()
+    del amp_meta[:]
+    streams, bounds, tx_sl = streams_saved, bounds_saved, tx_saved
+    su.op.amp = orig_amp
 
     # ---- timed: end to end from pinned host buffers
     for _ in range(2):
@@ -283,7 +331,7 @@ def gpu_arm(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "info_mbit_per_s": value * INFO_BITS / 1e6,
-            "config": {"workload": WORKLOAD, "codewords_per_step_per_gpu": B, "sigma": SIGMA, "amp_T": T,
+            "config": {"workload": WORKLOAD, "codewords_per_step_per_gpu": B, "sigma": SIGMA, "amp_T": T, "streams": S_,
                        "amp_mode": args.amp_mode + (" (fp64; z and FHT(beta) gathered from 27-bit fixed-point copies)"
                                                     if args.amp_mode == "fast" else " (fp64, reference add order)"),
                        "l2": "working set %.0f MB of beta per GPU per step exceeds the 126 MB L2" % (B * L * M * 8 / 1e6),
@@ -297,7 +345,8 @@ def gpu_arm(args):
             "roofline": {"bound": "hbm", "kernel": "sb::amp_kernel<9>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_codeword_iteration": bytes_per_iter,
-                         "launches_timed": n_amp_launch, "kernel_share_of_step": amp_ms / ms,
+                         "launches_timed": n_amp_launch, "kernel_share_of_step": share_serial,
+                         "kernel_busy_fraction_of_timed_region": amp_ms / ms,
                          "avg_launch_ms": amp_ms / max(n_amp_launch, 1),
                          "algorithmic_bytes_per_launch": alg_bytes / max(n_amp_launch, 1),
                          "co_limiter": "shared-memory data pipe (l1tex LSU wavefronts 81% of peak, profiles/r01_amp_kernel_ncu_full.csv)"},
@@ -321,9 +370,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1184, help="codewords per step per GPU (8 x 148 SMs: several waves even out the per-codeword early stop)")
+    ap.add_argument("--batch", type=int, default=2368,
+                    help="codewords per step per GPU (16 x 148 SMs; one CTA per codeword, several waves and streams "
+                         "even out the per-codeword early stop)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--streams", type=int, default=16, help="slices of the batch decoded on concurrent CUDA streams")
     ap.add_argument("--amp-mode", default="fast", choices=["strict", "fast"],
                     help="AMP arithmetic: strict = fp64 in the reference's add order; fast = fp64 with 32-bit "
                          "fixed-point gathers (include/sparc_b200.h SB_AMP_FAST); both pass the parity tests")
