@@ -139,6 +139,13 @@ int sb_sp2bp_llr_batch(const double *beta, long beta_stride, int beta_first, con
 int sb_bp2sp_prior_batch(const double *in, int ls, const double *beta_prev, int L, int M, int n, const double *Pl,
                          int mode, int B, double *out, void *stream);
 
+/* Denoiser of amp() alone (sparc_ldpc.py:214-219), for design matrices that are not the structured operator
+ * (dense Gaussian A: the two products are plain GEMMs done by the caller).  s[B][L*M] = beta + A^T z,
+ * tau2[B]; beta[B][L*M] out, sumsq[B][L] out = sum(beta_l^2) per section (0 for inactive codewords);
+ * active[B] (bytes) or NULL selects codewords. */
+int sb_section_softmax_batch(const double *s, const double *Pl, const double *tau2, const unsigned char *active, int L,
+                             int M, int n, int B, double *beta, double *sumsq, void *stream);
+
 /* idx[b][i] = argmax of section i of beta[b] (first maximum wins, sparc_ldpc.py:640-643) */
 int sb_argmax_batch(const double *beta, long beta_stride, int count, int M, int B, int *idx, long idx_stride,
                     void *stream);

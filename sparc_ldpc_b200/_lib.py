@@ -42,6 +42,7 @@ SIGNATURES = {
     "sb_amp_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_sp2bp_llr_batch": (_i, [_vp, _l, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _l, _vp]),
     "sb_bp2sp_prior_batch": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "sb_section_softmax_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sb_argmax_batch": (_i, [_vp, _l, _i, _i, _i, _vp, _l, _vp]),
     "sb_llr2idx_batch": (_i, [_vp, _l, _i, _i, _i, _vp, _l, _vp]),
     "sb_count_errors_batch": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

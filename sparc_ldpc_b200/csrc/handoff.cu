@@ -126,6 +126,35 @@ __global__ void bp2sp_prior_kernel(const double *__restrict__ app, int ls, const
     }
 }
 
+// Section-wise softmax denoiser of amp() for an arbitrary (dense) design matrix (sparc_ldpc.py:214-219):
+// beta = sqrt(n P_l) softmax_section(s sqrt(n P_l) / tau^2), and sum(beta^2) per section.  One warp per section;
+// codewords with active[b] == 0 are left untouched (per-codeword early stop).
+__global__ void section_softmax_kernel(const double *__restrict__ s, const double *__restrict__ Pl,
+                                       const double *__restrict__ tau2, const unsigned char *__restrict__ active, int L,
+                                       int M, int n, double *__restrict__ beta, double *__restrict__ sumsq) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int b = blockIdx.y, l = blockIdx.x * wpb + warp;
+    if (l >= L || (active && !active[b])) return;
+    const double rt = sqrt((double)n * Pl[l]), c2 = rt / tau2[b];
+    const double *src = s + ((size_t)b * L + l) * M;
+    double *dst = beta + ((size_t)b * L + l) * M;
+    double m = -INFINITY;
+    for (int j = lane; j < M; j += 32) m = fmax(m, src[j] * c2);
+    for (int d = 16; d; d >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, d));
+    double sum = 0.0;
+    for (int j = lane; j < M; j += 32) sum += exp(src[j] * c2 - m);
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const double sc = rt / sum;
+    double sq = 0.0;
+    for (int j = lane; j < M; j += 32) {
+        const double v = exp(src[j] * c2 - m) * sc;
+        dst[j] = v;
+        sq += v * v;
+    }
+    for (int d = 16; d; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+    if (lane == 0) sumsq[(size_t)b * L + l] = sq;  // per section: the caller adds them up deterministically
+}
+
 // idx = argmax of each section, first maximum wins (np.argmax).  One warp per section.
 __global__ void argmax_kernel(const double *__restrict__ beta, long beta_stride, int count, int M, int *idx,
                               long idx_stride) {
@@ -272,6 +301,20 @@ extern "C" int sb_bp2sp_prior_batch(const double *app, int ls, const double *bet
         SB_CUDA(cudaFuncSetAttribute(bp2sp_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bp2sp_prior_kernel<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(app, ls, beta_prev, L, M, ilog2(M), n, Pl,
                                                                       scale_by_power, input_is_prob, beta_init);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+extern "C" int sb_section_softmax_batch(const double *s, const double *Pl, const double *tau2,
+                                        const unsigned char *active, int L, int M, int n, int B, double *beta,
+                                        double *sumsq, void *stream) {
+    if (!s || !Pl || !tau2 || !beta || !sumsq || B < 0 || L <= 0 || M <= 0)
+        return fail(SB_EINVAL, "sb_section_softmax_batch: bad argument%s", "");
+    if (B == 0) return SB_OK;
+    SB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * (size_t)B * L, (cudaStream_t)stream));
+    const int wpb = 8;
+    dim3 grid((L + wpb - 1) / wpb, B);
+    section_softmax_kernel<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(s, Pl, tau2, active, L, M, n, beta, sumsq);
     SB_LAUNCHED();
     return SB_OK;
 }

@@ -158,6 +158,69 @@ class Operator:
         return AmpResult(beta, iters, n_exec, flags, tau2)
 
 
+class DenseOperator:
+    """Dense design matrix A [n, L*M] on the device (Gaussian-A mode; the reference's amp() accepts any Ab/Az
+    closures, sparc_ldpc.py:189).  The two products are fp64 library GEMMs (torch.matmul -> cuBLAS), the
+    denoiser is libsparc_b200's section softmax; the AMP loop runs on the host with a per-codeword active mask.
+    A hand-written tcgen05 GEMM with a split-bf16 scheme is the planned replacement."""
+
+    def __init__(self, A, L, M):
+        self.A = torch.as_tensor(A, dtype=F64).to(_dev()).contiguous()
+        self.n, LM = self.A.shape
+        self.L, self.M = int(L), int(M)
+        if LM != self.L * self.M:
+            raise ValueError("A must have L*M columns")
+        self.At = self.A.t().contiguous()
+
+    def Ab(self, beta):
+        return beta @ self.At          # [B, LM] x [LM, n]
+
+    def Az(self, z):
+        return z @ self.A              # [B, n] x [n, LM]
+
+    def amp(self, y, Pl, T, beta0=None, trace=False):
+        """sparc_ldpc.py:189-222 for a batch; returns AmpResult (iters = amp_test's t)."""
+        _chk(y, F64, "y")
+        _chk(Pl, F64, "Pl")
+        B, n = y.shape
+        L, M = self.L, self.M
+        dev = y.device
+        P = Pl.sum()
+        if beta0 is None:
+            beta = torch.zeros((B, L * M), dtype=F64, device=dev)
+            z = y.clone()
+        else:
+            beta = beta0.clone()
+            z = y - self.Ab(beta)
+        last_tau = torch.zeros(B, dtype=F64, device=dev)
+        active = torch.ones(B, dtype=torch.bool, device=dev)
+        iters = torch.full((B,), max(T - 1, 0), dtype=I32, device=dev)
+        n_exec = torch.zeros(B, dtype=I32, device=dev)
+        tau2_tr = torch.full((B, max(T, 1)), float("nan"), dtype=F64, device=dev) if trace else None
+        secsq = torch.empty((B, L), dtype=F64, device=dev)
+        for t in range(T):
+            tau = torch.sqrt((z * z).sum(dim=1) / n)
+            stop = active & (tau == last_tau)                      # exact-equality stop (:204)
+            iters = torch.where(stop, torch.full_like(iters, t), iters)
+            active = active & ~stop
+            if not bool(active.any()):
+                break
+            last_tau = torch.where(active, tau, last_tau)
+            tau2 = tau * tau
+            if trace:
+                tau2_tr[:, t] = torch.where(active, tau2, tau2_tr[:, t])
+            s = beta + self.Az(z)
+            act8 = active.to(torch.uint8)
+            check(_lib.lib().sb_section_softmax_batch(_p(s), _p(Pl), _p(tau2), _p(act8), L, M, int(n), B, _p(beta),
+                                                      _p(secsq), _stream()), "sb_section_softmax_batch")
+            sumsq = secsq.sum(dim=1)
+            z_new = y - self.Ab(beta) + (z / tau2[:, None]) * (P - sumsq / n)[:, None]
+            z = torch.where(active[:, None], z_new, z)
+            n_exec += active.to(I32)
+        flags = (~active).to(I32)
+        return AmpResult(beta, iters, n_exec, flags, tau2_tr)
+
+
 _OP_CACHE = {}
 
 

@@ -115,6 +115,25 @@ def sparc_transforms_shorter(L, M, n, ordering):
     return _closures(op, L, None)
 
 
+def sparc_transforms_gaussian(L, M, n, seed=0, A=None):
+    """Dense i.i.d. Gaussian design matrix A = RandomState(seed).randn(n, L*M)/sqrt(n) (BASELINE config 1;
+    the reference has no such matrix, but its amp() takes any closures) -> (Ab, Az, A)."""
+    if A is None:
+        A = np.random.RandomState(seed).randn(n, L * M) / np.sqrt(n)
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    op = E.DenseOperator(A, L, M)
+
+    def Ab(b):
+        return op.Ab(_to_dev(b, L * M)).cpu().numpy().reshape(-1, 1)
+
+    def Az(z):
+        return op.Az(_to_dev(z, n)).cpu().numpy().reshape(-1, 1)
+
+    for f in (Ab, Az):
+        f._sb_op, f._sb_rows, f._sb_L = op, None, L
+    return Ab, Az, A
+
+
 def amp(y, sigma_n, Pl, L, M, T, Ab, Az, beta=None):
     """AMP decoder with the reference signature (sparc_ldpc.py:189-222); sigma_n is unused, as there.
     Ab/Az must be closures returned by sparc_transforms[_shorter] of this module."""
@@ -134,6 +153,15 @@ def _amp_host(y, Pl, L, M, T, Ab, Az, beta):
     b0 = None if no_init else _to_dev(beta, L * M)
     res = op.amp(yd, Pld, T, beta0=b0)
     return res.beta.cpu().numpy().reshape(-1, 1), int(res.iters[0])
+
+
+def amp_gaussian_batch(op, y, Pl, T, beta0=None):
+    """Batched AMP over a DenseOperator: y [B, n] numpy -> (beta [B, L*M], iters [B])."""
+    yd = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64)).cuda()
+    Pld = torch.from_numpy(np.ascontiguousarray(Pl, dtype=np.float64)).cuda()
+    b0 = None if beta0 is None else torch.from_numpy(np.ascontiguousarray(beta0, dtype=np.float64)).cuda()
+    res = op.amp(yd, Pld, T, beta0=b0)
+    return res.beta.cpu().numpy(), res.iters.cpu().numpy()
 
 
 # ----------------------------------------------------------------------------------- section <-> bit maps

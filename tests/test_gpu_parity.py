@@ -203,6 +203,36 @@ def test_amp_c3_shape(Eng, S, k, mode):
     assert err_t < tol and worst < tol and err_p < tol
 
 
+def test_gaussian_design_matrix_c1(S, oracle):
+    """BASELINE configs[0]: plain SPARC AMP, L=128 M=4 R=1 P=2, dense Gaussian A.  Oracle = the reference's amp()
+    (oracle restatement) with numpy closures over the same matrix, as SURVEY section 8d prescribes."""
+    L, M, P, T = 128, 4, 2.0, 64
+    n = 256
+    Pl = P / L * np.ones(L)
+    Ab, Az, A = S.sparc_transforms_gaussian(L, M, n, seed=0)
+    rs = np.random.RandomState(4)
+    ys, idxs = [], []
+    for sigma in (0.708, 0.5, 0.9):
+        idx = rs.randint(0, M, L)
+        b0 = np.zeros(L * M)
+        b0[np.arange(L) * M + idx] = np.sqrt(n * Pl)
+        ys.append(A @ b0 + sigma * rs.randn(n))
+        idxs.append(idx)
+    beta, iters = S.amp_gaussian_batch(Ab._sb_op, np.array(ys), Pl, T)
+    for b in range(3):
+        tr = []
+        ref, t = oracle.amp(ys[b].reshape(-1, 1), Pl, L, M, T, lambda v: (A @ np.asarray(v).reshape(-1)).reshape(-1, 1),
+                            lambda v: (A.T @ np.asarray(v).reshape(-1)).reshape(-1, 1), trace=tr)
+        err = relinf(beta[b], ref.reshape(-1))
+        print("Gaussian C1 codeword %d: rel err beta %.2e, iterations %d (ref %d)" % (b, err, iters[b], t))
+        assert err < TIGHT and (abs(int(iters[b]) - t) <= 6 or int(iters[b]) == T - 1 or t == T - 1)
+        assert np.array_equal(beta[b].reshape(L, M).argmax(1), ref.reshape(L, M).argmax(1))
+    # the single-codeword reference signature takes the dense closures too
+    b1 = S.amp(ys[0].reshape(-1, 1), None, Pl, L, M, T, Ab, Az).reshape(-1)
+    assert relinf(b1, beta[0]) < 1e-12
+    assert Ab(beta[0]).shape == (n, 1) and relinf(Ab(beta[0]).reshape(-1), A @ beta[0]) < 1e-12
+
+
 def test_amp_batch_consistency_and_edge_cases(Eng):
     """A batch decodes each codeword exactly as a batch of one; T = 0 and empty section lists are no-ops."""
     g = golden("amp_small")
