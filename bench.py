@@ -375,7 +375,7 @@ def main():
                          "even out the per-codeword early stop)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--streams", type=int, default=16, help="slices of the batch decoded on concurrent CUDA streams")
+    ap.add_argument("--streams", type=int, default=8, help="slices of the batch decoded on concurrent CUDA streams")
     ap.add_argument("--amp-mode", default="fast", choices=["strict", "fast"],
                     help="AMP arithmetic: strict = fp64 in the reference's add order; fast = fp64 with 32-bit "
                          "fixed-point gathers (include/sparc_b200.h SB_AMP_FAST); both pass the parity tests")

@@ -39,7 +39,7 @@ SIGNATURES = {
     "sb_Ab_batch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "sb_Az_batch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "sb_onehot_apply_batch": (_i, [_vp, _vp, _vp, _vp, _d, _i, _vp, _vp]),
-    "sb_amp_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_amp_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_sp2bp_llr_batch": (_i, [_vp, _l, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _l, _vp]),
     "sb_bp2sp_prior_batch": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "sb_section_softmax_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -138,13 +138,15 @@ static AmpArgs base_args(const sb_operator *op, const int *sections, const int *
 
 extern "C" int sb_amp_batch(const sb_operator *op, const double *y, const double *Pl, const double *beta0,
                             const int *sections, const int *nsec, int B, int T, int mode, double *beta, int *iters,
-                            int *n_exec, unsigned *flags, double *tau2_trace, void *stream) {
+                            int *n_exec, unsigned *flags, double *tau2_trace, double *scratch, void *stream) {
     if (!op || !y || !Pl || !beta || !iters || !n_exec || !flags || B < 0 || T < 0)
         return fail(SB_EINVAL, "sb_amp_batch: null argument%s", "");
     if (mode != SB_AMP_STRICT && mode != SB_AMP_FAST) return fail(SB_EINVAL, "sb_amp_batch: unknown mode%s %ld", "", mode);
     if ((sections == nullptr) != (nsec == nullptr)) return fail(SB_EINVAL, "sb_amp_batch: sections and nsec go together%s", "");
+    if (mode == SB_AMP_FAST && op->pre && !scratch) return fail(SB_EINVAL, "sb_amp_batch: FAST mode needs a [B][n] scratch%s", "");
     if (B == 0) return SB_OK;
     AmpArgs a = base_args(op, sections, nsec);
+    a.zscratch = scratch;
     a.y = y; a.Pl = Pl; a.beta0 = beta0; a.beta = beta; a.tau2_trace = tau2_trace;
     a.iters = iters; a.n_exec = n_exec; a.flags = flags; a.T = T;
     return dispatch(op, a, B, mode == SB_AMP_FAST ? 3 : 0, nullptr, nullptr, (cudaStream_t)stream);

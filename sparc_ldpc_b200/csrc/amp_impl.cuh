@@ -178,7 +178,7 @@ struct AmpArgs {
     const uint16_t *fwd, *fwd8, *inv;
     const double *y, *Pl, *beta0;
     const int *sections, *nsec;
-    double *beta, *tau2_trace;
+    double *beta, *tau2_trace, *zscratch;
     int *iters, *n_exec;
     unsigned *flags;
     int L, n, Hp, NB, T;
@@ -189,7 +189,7 @@ struct SecCtx {  // per-iteration scalars of the section phase
 };
 
 // mode 0: AMP iteration (fold -> FHT -> softmax -> store beta -> FHT -> +-F)
-// mode 1: operator only (load beta -> FHT -> +-F), always fp64   [prologue z = y - A beta0, sb_Ab_batch]
+// mode 1: operator only (load beta -> FHT -> +-F)   [prologue z = y - A beta0, sb_Ab_batch]
 template <int LOGM, bool PRE, bool QUANT>
 __device__ __forceinline__ void section_phase(int mode, bool first_zero, const AmpArgs &a, const double *bsrc,
                                               double *bdst, int sec, int q, const void *zsv, char *Fbytes, int slot,
@@ -241,7 +241,7 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
         }
     }
     fht_team<LOGM>(x, q, tmask);
-    if (QUANT && mode == 0) {
+    if (QUANT) {
         int *Fp = reinterpret_cast<int *>(Fbytes + slot_offset<LOGM, 2>(slot));
         int *Fn = reinterpret_cast<int *>(Fbytes + slot_offset<LOGM, 2>(slot) + (1 << SBQ));
 #pragma unroll
@@ -388,7 +388,7 @@ __device__ __forceinline__ void operator_pass(int mode, bool first_zero, const A
                                               double &gmax, double &lmin) {
     constexpr int M = TeamCfg<LOGM>::M, TEAM = TeamCfg<LOGM>::TEAM;
     const int tm = threadIdx.x / TEAM, q = threadIdx.x % TEAM;
-    const bool qpass = QUANT && mode == 0;
+    const bool qpass = QUANT;
     for (int k = threadIdx.x; k < a.n; k += blockDim.x) acc_s[k] = 0.0;
     for (int g0 = 0; g0 < La; g0 += W) {
         const int sidx = g0 + tm;
@@ -416,8 +416,9 @@ __device__ __forceinline__ void operator_pass(int mode, bool first_zero, const A
     }
 }
 
-// shared-memory carve-up.  strict: z fp64 [n+1 (zero word)] | acc | F | red | sec
-//                          quant : zq int32 [n+1 (zero word)] | z fp64 [n] | acc | F (fp64-sized: prologue) | red | sec
+// shared-memory carve-up.  strict: z fp64 [n+1 (zero word)] | acc | F (fp64 +-) | red | sec
+//                          quant : zq int32 [n+1 (zero word)] | acc | F (int32 +-) | red | sec   (fp64 z lives in a
+//                                  per-codeword global scratch row: it is only touched element-wise)
 template <int LOGM, bool QUANT>
 struct Smem {
     double *zf, *acc, *red;
@@ -426,11 +427,10 @@ struct Smem {
     int *sec;
     __host__ __device__ static size_t f_bytes(int W) {
         const int regions = (W + TeamCfg<LOGM>::SPR - 1) / TeamCfg<LOGM>::SPR;
-        return (size_t)regions * (4 << TeamCfg<LOGM>::SBQ);
+        return (size_t)regions * ((QUANT ? 2 : 4) << TeamCfg<LOGM>::SBQ);
     }
     __host__ __device__ static size_t bytes(int n, int W) {
-        size_t b = QUANT ? sizeof(int) * (size_t)pad4(n + 1) + sizeof(double) * (size_t)pad2(n)
-                         : sizeof(double) * (size_t)pad2(n + 1);
+        size_t b = QUANT ? sizeof(int) * (size_t)pad4(n + 1) : sizeof(double) * (size_t)pad2(n + 1);
         b += sizeof(double) * (size_t)pad2(n);  // acc
         b += f_bytes(W);
         b += sizeof(double) * 40 + sizeof(int) * (size_t)(W + 2);
@@ -439,8 +439,8 @@ struct Smem {
     __device__ Smem(unsigned char *raw, int n, int W) {
         if (QUANT) {
             zq = reinterpret_cast<int *>(raw);
-            zf = reinterpret_cast<double *>(zq + pad4(n + 1));
-            acc = zf + pad2(n);
+            zf = nullptr;
+            acc = reinterpret_cast<double *>(zq + pad4(n + 1));
         } else {
             zq = nullptr;
             zf = reinterpret_cast<double *>(raw);
@@ -461,7 +461,8 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, b = blockIdx.x;
     Smem<LOGM, QUANT> sm(smem_raw, n, W);
-    double *zf = sm.zf, *acc_s = sm.acc, *red = sm.red;
+    double *zf = QUANT ? a.zscratch + (size_t)b * n : sm.zf;  // every thread only touches its own k = tid + j*NT
+    double *acc_s = sm.acc, *red = sm.red;
     if (threadIdx.x == 0) {
         if (QUANT) sm.zq[n] = 0; else zf[n] = 0.0;
     }
@@ -501,9 +502,24 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
     // |F| <= sqrt(n P_l) <= cmax; the 1e-6 margin keeps |F_q| strictly below 2^27 so 16-term int32 sums cannot overflow
     const double fscale_q = scalbn(1.0, 27 - ceil_exp(cmax * (1.0 + 1e-6)));
 
-    if (a.beta0 != nullptr) {  // z = y - A beta0   (sparc_ldpc.py:197-198), always in fp64
-        operator_pass<LOGM, PRE, QUANT>(1, false, a, a.beta0 + (size_t)b * a.L * M, beta, act, La, zsv, acc_s, sm.F,
-                                        sm.sec, W, cx, nd, sq, gmax, lmin);
+    if (a.beta0 != nullptr) {  // z = y - A beta0   (sparc_ldpc.py:197-198)
+        const double *b0 = a.beta0 + (size_t)b * a.L * M;
+        if (QUANT) {  // |FHT_M(beta0_l)| <= sum_j |beta0_l[j]|: one streaming pass gives the fixed-point scale
+            constexpr int TEAM = TeamCfg<LOGM>::TEAM;
+            const unsigned tmask = team_mask<TEAM>();
+            const int tm = threadIdx.x / TEAM, q = threadIdx.x % TEAM;
+            double bound = 0.0;
+            for (int sidx = tm; sidx < La; sidx += blockDim.x / TEAM) {
+                double s1 = 0.0;
+                for (int j = q; j < M; j += TEAM) s1 += fabs(b0[(size_t)sidx * M + j]);
+#pragma unroll
+                for (int d = TEAM / 2; d >= 1; d >>= 1) s1 += __shfl_xor_sync(tmask, s1, d);
+                bound = fmax(bound, s1);
+            }
+            cx.fscale = scalbn(1.0, 27 - ceil_exp(block_max(bound, red) * (1.0 + 1e-6)));
+        }
+        operator_pass<LOGM, PRE, QUANT>(1, false, a, b0, beta, act, La, zsv, acc_s, sm.F, sm.sec, W, cx, nd, sq, gmax,
+                                        lmin);
         for (int k = threadIdx.x; k < n; k += blockDim.x) zf[k] = y[k] - acc_s[k] / rt_n;
     } else {
         for (int k = threadIdx.x; k < n; k += blockDim.x) zf[k] = y[k];
@@ -607,11 +623,14 @@ __global__ void __launch_bounds__(512, 1) Az_kernel(AmpArgs a, int W, const doub
     }
 }
 
-// threads per CTA: as many teams as fit in shared memory (<= 512 threads), never more teams than sections
+// threads per CTA.  Default: 512 (one CTA per SM); with fixed-point gathers the state is small enough for TWO
+// 256-thread CTAs per SM, whose gather (shared-memory pipe) and transform (fp64 / issue) phases then overlap.
+// Never more teams than sections, never more shared memory than 227 KB.
 template <int LOGM, bool QUANT>
 static int pick_threads(int n, int L, size_t *smem_out, int *W_out) {
     constexpr int TEAM = TeamCfg<LOGM>::TEAM;
     int nt = 512;
+    if (QUANT && TEAM == 32 && 2 * (Smem<LOGM, QUANT>::bytes(n, 256 / TEAM) + 1024) <= 227 * 1024) nt = 256;
     const char *env = getenv("SB_AMP_THREADS");
     if (env) nt = atoi(env);
     if (nt > 512) nt = 512;
