@@ -158,6 +158,15 @@ int sb_count_errors_batch(const int *a, const int *t, int count, int B, int *err
 /* beta[b][l*M + idx[b][l]] = sqrt(n*Pl[l]), zero elsewhere (sparc_ldpc.py:840-843); idx < 0: all-zero section */
 int sb_onehot_beta_batch(const int *idx, const double *Pl, int n, int L, int M, int B, double *beta, void *stream);
 
+/* On-device input generation.  Systematic QC-LDPC encoder of ldpc.py:790-850: proto[Mp][Np]
+ * (device, shift or -1), toff = the single odd-multiplicity shift (mod z) of protograph column Np-Mp (ldpc.py:823-835);
+ * info[B][(Np-Mp)*z] bytes 0/1 -> x[B][Np*z] bytes 0/1. */
+int sb_ldpc_encode_batch(const int *proto, int Mp, int Np, int z, int toff, const unsigned char *info, int B,
+                         unsigned char *x, void *stream);
+/* idx[b][i] = MSB-first value of bits[b][i*logM .. i*logM+logM) (bytes 0/1)   (bits2indices, sparc_ldpc.py:317-341) */
+int sb_bits2idx_batch(const unsigned char *bits, long bits_stride, int count, int M, int B, int *idx, long idx_stride,
+                      void *stream);
+
 /* Threshold peel (amp_exit.py:85-116): post[B][L*M] section posteriors; sections l >= L-ls with exactly one
  * entry > threshold are hard decided.  hard_idx[B][L] = decided index or -1; act[B][L] = ascending list of the
  * remaining sections, nact[B] its length. */

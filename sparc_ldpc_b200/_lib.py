@@ -47,6 +47,8 @@ SIGNATURES = {
     "sb_llr2idx_batch": (_i, [_vp, _l, _i, _i, _i, _vp, _l, _vp]),
     "sb_count_errors_batch": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "sb_onehot_beta_batch": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "sb_ldpc_encode_batch": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "sb_bits2idx_batch": (_i, [_vp, _l, _i, _i, _i, _vp, _l, _vp]),
     "sb_threshold_peel_batch": (_i, [_vp, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp]),
     "sb_exit_hist_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp]),
 }

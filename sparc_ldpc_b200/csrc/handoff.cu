@@ -243,6 +243,58 @@ __global__ void onehot_beta_kernel(const int *__restrict__ idx, const double *__
     }
 }
 
+// Systematic QC-LDPC encoder (ldpc/py/ldpc.py:790-850), one CTA per codeword, bits as bytes in shared memory.
+// proto[Mp][Np] (shift or -1); info[B][Kp*z] -> x[B][Np*z]; toff = the single odd-multiplicity shift of column Kp.
+__global__ void ldpc_encode_kernel(const int *__restrict__ proto, int Mp, int Np, int z, int toff,
+                                   const unsigned char *__restrict__ info, unsigned char *__restrict__ x) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Kp = Np - Mp, b = blockIdx.x;
+    unsigned char *xs = smem_raw;              // [Np][z]
+    unsigned char *syn = xs + (size_t)Np * z;  // [Mp][z] systematic part of every block-row
+    for (int i = threadIdx.x; i < Kp * z; i += blockDim.x) xs[i] = info[(size_t)b * Kp * z + i] & 1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < Mp * z; i += blockDim.x) {
+        const int r = i / z, k = i % z;
+        unsigned char acc = 0;
+        for (int c = 0; c < Kp; c++) {
+            const int sft = proto[r * Np + c];
+            if (sft >= 0) acc ^= xs[c * z + (k + sft) % z];  // np.roll(x_c, -shift)[k]
+        }
+        syn[i] = acc;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < z; k += blockDim.x) {  // first parity block: roll(sum of all rows, toff)
+        const int src = ((k - toff) % z + z) % z;
+        unsigned char acc = 0;
+        for (int r = 0; r < Mp; r++) acc ^= syn[r * z + src];
+        xs[Kp * z + k] = acc;
+    }
+    __syncthreads();
+    for (int r = 0; r < Mp - 1; r++) {  // back-substitution down the dual diagonal
+        for (int k = threadIdx.x; k < z; k += blockDim.x) {
+            unsigned char acc = syn[r * z + k];
+            for (int c = 0; c <= r; c++) {
+                const int sft = proto[r * Np + Kp + c];
+                if (sft >= 0) acc ^= xs[(Kp + c) * z + (k + sft) % z];
+            }
+            xs[(Kp + r + 1) * z + k] = acc;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < Np * z; i += blockDim.x) x[(size_t)b * Np * z + i] = xs[i];
+}
+
+// idx[b][i] = MSB-first value of logM consecutive bits (bytes 0/1)   (sparc_ldpc.py:317-341)
+__global__ void bits2idx_kernel(const unsigned char *__restrict__ bits, long bits_stride, int count, int logM, int *idx,
+                                long idx_stride) {
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const unsigned char *src = bits + (size_t)b * bits_stride + (size_t)i * logM;
+    int v = 0;
+    for (int j = 0; j < logM; j++) v = (v << 1) | (src[j] & 1);
+    idx[(size_t)b * idx_stride + i] = v;
+}
+
 // np.histogram(E[X == +-1], bins=edges): left-closed bins, last bin closed on the right.
 __global__ void exit_hist_kernel(const double *__restrict__ E, const int *__restrict__ X, int len,
                                  const double *__restrict__ edges, int nedges, unsigned long long *counts) {
@@ -369,6 +421,31 @@ extern "C" int sb_onehot_beta_batch(const int *idx, const double *Pl, int n, int
     const size_t LM = (size_t)L * M;
     dim3 grid((unsigned)((LM + 255) / 256 > 1184 ? 1184 : (LM + 255) / 256), B);
     onehot_beta_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, Pl, n, L, M, beta);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+extern "C" int sb_ldpc_encode_batch(const int *proto, int Mp, int Np, int z, int toff, const unsigned char *info, int B,
+                                    unsigned char *x, void *stream) {
+    if (!proto || !info || !x || Mp <= 0 || Np <= Mp || z <= 0 || B < 0)
+        return fail(SB_EINVAL, "sb_ldpc_encode_batch: bad argument%s", "");
+    if (B == 0) return SB_OK;
+    const size_t smem = (size_t)(Np + Mp) * z;
+    if (smem > 227 * 1024) return fail(SB_EINVAL, "sb_ldpc_encode_batch: code too large for shared memory%s", "");
+    if (smem > 48 * 1024)
+        SB_CUDA(cudaFuncSetAttribute(ldpc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ldpc_encode_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(proto, Mp, Np, z, toff, info, x);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+extern "C" int sb_bits2idx_batch(const unsigned char *bits, long bits_stride, int count, int M, int B, int *idx,
+                                 long idx_stride, void *stream) {
+    if (!bits || !idx || B < 0 || count < 0 || M < 2 || (M & (M - 1)))
+        return fail(SB_EINVAL, "sb_bits2idx_batch: bad argument%s", "");
+    if (B == 0 || count == 0) return SB_OK;
+    dim3 grid((count + 127) / 128, B);
+    bits2idx_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(bits, bits_stride, count, ilog2(M), idx, idx_stride);
     SB_LAUNCHED();
     return SB_OK;
 }

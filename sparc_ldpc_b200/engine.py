@@ -358,6 +358,35 @@ def onehot_beta(idx, Pl, n, L, M):
     return beta
 
 
+def ldpc_encode(code, info):
+    """Device QC-LDPC encoder: info [B, K] uint8 (CUDA) -> codewords [B, N] uint8 (ldpc.py:790-850)."""
+    if not (info.is_cuda and info.dtype == torch.uint8 and info.is_contiguous()):
+        raise ValueError("info must be a contiguous CUDA uint8 tensor")
+    Mp, Np, Kp, toff = code._encoder_plan()
+    z = int(code.z)
+    if info.shape[1] != Kp * z:
+        raise NameError("information word length not compatible with proto and z")
+    if getattr(code, "_proto_dev", None) is None or code._proto_dev.device != info.device:
+        code._proto_dev = torch.from_numpy(np.ascontiguousarray(code.proto, dtype=np.int32)).to(info.device)
+    B = info.shape[0]
+    x = torch.empty((B, Np * z), dtype=torch.uint8, device=info.device)
+    check(_lib.lib().sb_ldpc_encode_batch(_p(code._proto_dev), Mp, Np, z, toff, _p(info), B, _p(x), _stream()),
+          "sb_ldpc_encode_batch")
+    return x
+
+
+def bits2idx(bits, count, M, out=None):
+    """MSB-first section indices of a CUDA uint8 bit tensor [B, >= count*logM] (sparc_ldpc.py:317-341)."""
+    if not (bits.is_cuda and bits.dtype == torch.uint8 and bits.stride(1) == 1):
+        raise ValueError("bits must be a CUDA uint8 tensor with unit inner stride")
+    B = bits.shape[0]
+    if out is None:
+        out = torch.empty((B, count), dtype=I32, device=bits.device)
+    check(_lib.lib().sb_bits2idx_batch(bits.data_ptr(), bits.stride(0), int(count), int(M), B, out.data_ptr(),
+                                       out.stride(0), _stream()), "sb_bits2idx_batch")
+    return out
+
+
 def threshold_peel(post, L, M, ls, threshold):
     """amp_exit.py:85-106 -> (hard_idx [B, L], act [B, L], nact [B])."""
     _chk(post, F64, "post")

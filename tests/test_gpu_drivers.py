@@ -186,3 +186,33 @@ def test_errors_mirror_the_reference():
         S.amp(np.zeros((24, 1)), None, np.ones(8), 8, 16, 4, lambda b: b, lambda z: z)
     with pytest.raises(AssertionError):          # LDPC must cover whole sections (sparc_ldpc.py:416)
         S.soft_amp_ldpc_sim(S.SPARCParams(64, 32, 0.5, 4.0, 1, 8), S.LDPCParams("802.16", "5/6", 8), 1)
+
+
+def test_device_encoder_bit_exact_and_throughput_mode():
+    """On-device input generation: the LDPC encoder kernel equals the host encoder bit for bit; a
+    throughput-mode point is reproducible and error-free at high SNR."""
+    from sparc_ldpc_b200 import engine as E, ldpc, montecarlo as MC, sparc_ldpc as S
+    rs = np.random.RandomState(2)
+    for args in [("802.16", "1/2", 33), ("802.16", "5/6", 192), ("802.16", "2/3", 27, "B"), ("802.16", "3/4", 54, "A"),
+                 ("802.11n", "1/2", 81), ("802.11n", "5/6", 27)]:
+        c = ldpc.code(*args)
+        U = rs.randint(0, 2, (5, c.K)).astype(np.uint8)
+        X = E.ldpc_encode(c, torch.from_numpy(U).cuda()).cpu().numpy()
+        assert np.array_equal(X, c.encode_batch(U))
+    bits = rs.randint(0, 2, (3, 40)).astype(np.uint8)
+    idx = E.bits2idx(torch.from_numpy(bits).cuda(), 8, 32).cpu().numpy()
+    assert idx.tolist() == [S.bits2indices(b, 32) for b in bits]
+    sp = S.SPARCParams(L=64, M=8, sigma=0.8, p=4.0, r=1, t=64)
+    lp = S.LDPCParams("802.16", "5/6", 8)
+    a = MC.ber_point(sp, lp, 50, flow="soft", seed=3, batch=32)
+    b = MC.ber_point(sp, lp, 50, flow="soft", seed=3, batch=32)
+    assert a == b and a["n_codewords"] == 50 and len(a["ber_amp"]) == 3 and len(a["ber_ldpc"]) == 2
+    assert 0 < a["ber_amp"][0] < 0.1 and a["amp_iterations"] > 0 and a["bp_iterations"] >= 0
+    c2 = MC.ber_point(S.SPARCParams(L=64, M=8, sigma=0.3, p=4.0, r=1, t=64), lp, 40, flow="hard", seed=1)
+    assert c2["ber_amp"] == [0.0, 0.0] and c2["ber_ldpc"] == [0.0] and c2["block_errors_amp"] == [0, 0]
+    for fl in ("plain", "originalHard", "threshold"):
+        lp2 = S.LDPCParams("802.16", "5/6", 4) if fl == "originalHard" else lp
+        r = MC.ber_point(sp, lp2, 20, flow=fl, seed=5, soft_iter=2, threshold=0.6, amp_mode="fast")
+        assert r["n_codewords"] == 20 and all(0 <= v < 0.2 for v in r["ber_amp"])
+    w = MC.waterfall_device(S.SPARCParams(L=64, M=8, sigma=None, p=4.0, r=1, t=64), lp, [6.0, 12.0], 30, flow="soft")
+    assert w[0]["ber_amp"][0] >= w[1]["ber_amp"][0] and w[1]["sigma"] < w[0]["sigma"]

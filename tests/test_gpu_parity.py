@@ -233,6 +233,41 @@ def test_gaussian_design_matrix_c1(S, oracle):
     assert Ab(beta[0]).shape == (n, 1) and relinf(Ab(beta[0]).reshape(-1), A @ beta[0]) < 1e-12
 
 
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_c5_shape_against_oracle(Eng, oracle, mode):
+    """BASELINE configs[4] shape: L = 768, M = 512, r = 5/6 -> n = 8294, w = 16384 (two 16-entry blocks per bin,
+    smaller section groups because z no longer leaves room for 16 transform buffers)."""
+    L, M, P, r = 768, 512, 1.8, 5 / 6
+    n = int(L * np.log2(M) / r)
+    assert n == 8294
+    Pl = P / L * np.ones(L)
+    op = Eng.get_operator(L, M, n, 0)
+    Abo, Azo, ordo = oracle.sparc_transforms(L, M, n)
+    assert np.array_equal(op.ordering, ordo)
+    rs = np.random.RandomState(8)
+    if mode == "strict":
+        b = rs.randn(L * M)
+        z = rs.randn(n)
+        assert np.array_equal(op.Ab(cu(b.reshape(1, -1))).cpu().numpy().reshape(-1), Abo(b).reshape(-1))
+        assert np.array_equal(op.Az(cu(z.reshape(1, -1))).cpu().numpy().reshape(-1), Azo(z).reshape(-1))
+    idx = rs.randint(0, M, L)
+    b0 = np.zeros(L * M)
+    b0[np.arange(L) * M + idx] = np.sqrt(n * Pl)
+    y = Abo(b0) + 0.55 * rs.randn(n, 1)
+    T = 6
+    tr = []
+    ref, _ = oracle.amp(y, Pl, L, M, T, Abo, Azo, trace=tr)
+    res = op.amp(cu(y.reshape(1, -1)), cu(Pl), T, trace=True, mode=mode)
+    err_b = relinf(res.beta.cpu().numpy().reshape(-1), ref.reshape(-1))
+    err_t = relinf(res.tau2.cpu().numpy().reshape(-1)[:T], np.array([x[0] for x in tr]))
+    print("C5 [%s]: rel err beta %.2e tau2 %.2e after %d iterations" % (mode, err_b, err_t, T))
+    assert err_b < MODE_TOL[mode] and err_t < MODE_TOL[mode]
+    # warm start from the oracle's state (prologue z = y - A beta0 on the quantised or strict path)
+    ref2, _ = oracle.amp(y, Pl, L, M, 2, Abo, Azo, ref)
+    res2 = op.amp(cu(y.reshape(1, -1)), cu(Pl), 2, beta0=cu(ref.reshape(1, -1)), mode=mode)
+    assert relinf(res2.beta.cpu().numpy().reshape(-1), ref2.reshape(-1)) < MODE_TOL[mode]
+
+
 def test_amp_batch_consistency_and_edge_cases(Eng):
     """A batch decodes each codeword exactly as a batch of one; T = 0 and empty section lists are no-ops."""
     g = golden("amp_small")
