@@ -84,6 +84,12 @@ int sb_bp_batch(const sb_graph *g, int rule, const double *ch, int B, double *ap
 typedef struct sb_operator sb_operator;
 int sb_operator_create(const uint32_t *ordering_host, int L, int M, int n, sb_operator **out);
 void sb_operator_destroy(sb_operator *op);
+/* Host-only self check of the FAST-mode lookup tables (no GPU needed): rebuilds them from `ordering_host` and
+ * verifies that they are a reordering of the operator of sparc_ldpc.py:110-134 (every bin lists exactly its
+ * (row, sign) terms, every (16-section chunk, row) exactly its 16 (section, column, sign) terms).
+ * stats[4] (may be NULL) = fold steps, fold shared-memory wavefronts, gather steps, gather wavefronts of the
+ * bank-conflict model.  Returns 0 = verified, 1 = shape has no FAST tables, <0 = error. */
+int sb_fast_tables_check(const uint32_t *ordering_host, int L, int M, int n, long *stats);
 
 /* pyfht.fht_inplace (sparc_ldpc.py:14-29, :69, :76): HOST pointer, N a power of two, transformed in place. */
 int sb_fht_inplace_host(double *x, long N);

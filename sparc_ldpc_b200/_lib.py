@@ -35,6 +35,7 @@ SIGNATURES = {
     "sb_bp_batch": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _d, _vp]),
     "sb_operator_create": (_i, [_vp, _i, _i, _i, ct.POINTER(_vp)]),
     "sb_operator_destroy": (None, [_vp]),
+    "sb_fast_tables_check": (_i, [_vp, _i, _i, _i, _vp]),
     "sb_fht_inplace_host": (_i, [_vp, _l]),
     "sb_Ab_batch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "sb_Az_batch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),

@@ -1,6 +1,11 @@
 // amp.cu -- host side of the SPARC design operator / AMP entry points: table construction and dispatch.
 // The kernels live in amp_impl.cuh and are instantiated per section size in amp_inst_*.cu.
 #include "amp_impl.cuh"
+#include "sched.h"
+
+#include <functional>
+#include <thread>
+#include <vector>
 
 namespace sb {
 
@@ -70,6 +75,109 @@ static int dispatch(const sb_operator *op, AmpArgs a, int B, int which, const do
 
 static int sign_bit(int logM) { return logM + 2 + (logM >= 10 ? 2 : 3); }
 
+// ---- FAST-mode tables: conflict-free orderings of the two shared-memory gathers (sched.h) -------------------
+// Host-only; sb_operator_create uploads the result, sb_fast_tables_check (tests) verifies it without a GPU.
+struct FastTables {
+    int qok = 0, qpre = 0, qneg = 0, G16 = 0;
+    std::vector<uint16_t> invq, fwd16;
+    long fold_steps = 0, fold_wavefronts = 0, gather_steps = 0, gather_wavefronts = 0;  // bank-conflict model
+};
+
+static int team_lanes(int M) { return M >= 128 ? 32 : (M >= 4 ? M / 4 : 1); }
+
+static void parallel_for(int count, const std::function<void(int, int)> &body) {
+    int nt = (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 16) nt = 16;
+    if (nt > count) nt = count;
+    if (nt <= 1) { body(0, count); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) {
+        const int a = (int)((long)count * t / nt), b = (int)((long)count * (t + 1) / nt);
+        th.emplace_back(body, a, b);
+    }
+    for (auto &x : th) x.join();
+}
+
+static void build_fast_tables(const uint32_t *ordering, int L, int M, int n, int Hp, FastTables &ft) {
+    const int logM = ilog2(M), SBQ = sign_bit(logM), TEAM = team_lanes(M), EPT = M / TEAM;
+    ft.qneg = n + 32;
+    if (2L * n + 32 > 65535) return;  // offsets do not fit 16 bits: FAST falls back to STRICT
+    ft.qok = 1;
+    ft.qpre = ((2L * n + 32) * 4 <= 65535) ? 1 : 0;
+    const int osh = ft.qpre ? 2 : 0;
+    ft.invq.assign((size_t)L * M * Hp, 0);
+    std::vector<long> stat((size_t)L * 2, 0);
+    // fold: pool = (section, e): lane q of the team owns bin e*TEAM + q and reads one term per step
+    parallel_for(L, [&](int l0, int l1) {
+        PoolScheduler ps;
+        std::vector<PoolEdge> E;
+        std::vector<std::vector<int>> bins(M);
+        std::vector<int> used((size_t)Hp * 32);
+        for (int l = l0; l < l1; l++) {
+            for (auto &b : bins) b.clear();
+            for (int k = 0; k < n; k++) {
+                const uint32_t r = ordering[(size_t)l * n + k];
+                const int neg = __builtin_popcount(r / M) & 1;  // sign of block hi in the fold tree = (-1)^popcount(hi)
+                bins[r % M].push_back(neg ? ft.qneg + k : k);
+            }
+            for (int e = 0; e < EPT; e++) {
+                E.clear();
+                for (int q = 0; q < TEAM; q++)
+                    for (int o : bins[e * TEAM + q]) E.push_back(PoolEdge{q, o & 31, o, 0});
+                ps.run(E, Hp);
+                PoolScheduler::improve(E, Hp);
+                stat[(size_t)l * 2] += Hp;
+                stat[(size_t)l * 2 + 1] += PoolScheduler::cost(E, Hp);
+                std::fill(used.begin(), used.end(), 0);
+                for (const PoolEdge &pe : E) used[(size_t)pe.step * 32 + pe.bank] = 1;
+                // idle slots read a zero word that lies in a bank no real term of the step uses
+                for (int t = 0; t < Hp; t++) {
+                    int fb = 0;
+                    for (int b = 0; b < 32; b++) if (!used[(size_t)t * 32 + b]) { fb = b; break; }
+                    const int zero_word = n + ((fb - n) & 31);  // word in [n, n+32) with bank fb
+                    for (int q = 0; q < TEAM; q++)
+                        ft.invq[((size_t)l * M + e * TEAM + q) * Hp + t] = (uint16_t)(zero_word << osh);
+                }
+                for (const PoolEdge &pe : E)
+                    ft.invq[((size_t)l * M + e * TEAM + pe.lane) * Hp + pe.step] = (uint16_t)(pe.id << osh);
+            }
+        }
+    });
+    for (int l = 0; l < L; l++) { ft.fold_steps += stat[(size_t)l * 2]; ft.fold_wavefronts += stat[(size_t)l * 2 + 1]; }
+    // gather: pool = (chunk of 16 sections, warp row of 32 consecutive k); lane k%32 reads one section per step
+    if (logM > 9) return;
+    ft.G16 = L / 16;
+    if (ft.G16 == 0) return;
+    ft.fwd16.assign((size_t)ft.G16 * n * 16, 0);
+    const int SPR = 8;
+    std::vector<long> gstat((size_t)ft.G16 * 2, 0);
+    parallel_for(ft.G16, [&](int g0, int g1) {
+        PoolScheduler ps;
+        std::vector<PoolEdge> E;
+        for (int g = g0; g < g1; g++)
+            for (int k0 = 0; k0 < n; k0 += 32) {
+                E.clear();
+                const int nl = (n - k0 < 32) ? n - k0 : 32;
+                for (int q = 0; q < nl; q++)
+                    for (int i = 0; i < 16; i++) {
+                        const uint32_t r = ordering[(size_t)(g * 16 + i) * n + k0 + q];
+                        const uint32_t lo = r % M, sg = __builtin_popcount(r / M) & 1;
+                        const uint32_t off = (uint32_t)(i / SPR) * (2u << SBQ) + (uint32_t)(i % SPR) * ((uint32_t)M << 2) +
+                                             (lo << 2) + (sg << SBQ);
+                        E.push_back(PoolEdge{q, (int)((off >> 2) & 31), (int)off, 0});
+                    }
+                ps.run(E, 16);
+                PoolScheduler::improve(E, 16);
+                gstat[(size_t)g * 2] += 16;
+                gstat[(size_t)g * 2 + 1] += PoolScheduler::cost(E, 16);
+                for (const PoolEdge &pe : E)
+                    ft.fwd16[((size_t)g * n + k0 + pe.lane) * 16 + pe.step] = (uint16_t)pe.id;
+            }
+    });
+    for (int g = 0; g < ft.G16; g++) { ft.gather_steps += gstat[(size_t)g * 2]; ft.gather_wavefronts += gstat[(size_t)g * 2 + 1]; }
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -105,10 +213,28 @@ extern "C" int sb_operator_create(const uint32_t *ordering, int L, int M, int n,
             h8[((size_t)(l >> 3) * n + k) * 8 + (l & 7)] = fe;
             hi[((size_t)l * M + lo) * op->Hp + c] = (uint16_t)(op->pre ? k * 4 : k);
         }
-    op->fwd = nullptr; op->inv = nullptr; op->fwd8 = nullptr;
+    op->fwd = nullptr; op->inv = nullptr; op->fwd8 = nullptr; op->invq = nullptr; op->fwd16 = nullptr;
+    {   // FAST-mode tables (scheduled gathers)
+        FastTables ft;
+        build_fast_tables(ordering, L, M, n, op->Hp, ft);
+        op->qok = ft.qok; op->qpre = ft.qpre; op->qneg = ft.qneg; op->G16 = ft.G16;
+        if (ft.qok) {
+            cudaError_t q1 = cudaMalloc(&op->invq, ft.invq.size() * 2), q2 = cudaSuccess;
+            if (q1 == cudaSuccess) q1 = cudaMemcpy(op->invq, ft.invq.data(), ft.invq.size() * 2, cudaMemcpyHostToDevice);
+            if (ft.G16 > 0) {
+                q2 = cudaMalloc(&op->fwd16, ft.fwd16.size() * 2);
+                if (q2 == cudaSuccess) q2 = cudaMemcpy(op->fwd16, ft.fwd16.data(), ft.fwd16.size() * 2, cudaMemcpyHostToDevice);
+            }
+            if (q1 != cudaSuccess || q2 != cudaSuccess) {
+                cudaFree(op->invq); cudaFree(op->fwd16); free(hf); free(hi); free(h8); delete op;
+                return fail(SB_ENOMEM, "sb_operator_create: cudaMalloc (fast tables) failed%s", "");
+            }
+        }
+    }
     cudaError_t e1 = cudaMalloc(&op->fwd, nf * 2), e2 = cudaMalloc(&op->inv, ni * 2), e3 = cudaMalloc(&op->fwd8, n8 * 2);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-        cudaFree(op->fwd); cudaFree(op->inv); cudaFree(op->fwd8); free(hf); free(hi); free(h8); delete op;
+        cudaFree(op->fwd); cudaFree(op->inv); cudaFree(op->fwd8); cudaFree(op->invq); cudaFree(op->fwd16);
+        free(hf); free(hi); free(h8); delete op;
         return fail(SB_ENOMEM, "sb_operator_create: cudaMalloc failed%s", "");
     }
     e1 = cudaMemcpy(op->fwd, hf, nf * 2, cudaMemcpyHostToDevice);
@@ -125,13 +251,65 @@ extern "C" void sb_operator_destroy(sb_operator *op) {
     cudaFree(op->fwd);
     cudaFree(op->fwd8);
     cudaFree(op->inv);
+    cudaFree(op->invq);
+    cudaFree(op->fwd16);
     delete op;
+}
+
+// Test hook (no GPU needed): builds the FAST-mode tables on the host and verifies that they are a reordering of
+// the operator -- every bin of every section lists exactly its (k, sign) terms, every (16-section chunk, row)
+// lists exactly its 16 (slot, lo, sign) terms.  stats[0..3] = fold steps, fold wavefronts, gather steps, gather
+// wavefronts of the bank-conflict model (wavefronts / steps = 1 means conflict-free).
+extern "C" int sb_fast_tables_check(const uint32_t *ordering, int L, int M, int n, long *stats) {
+    if (!ordering || L <= 0 || n <= 0 || M < 2 || (M & (M - 1)) || M > 1024 || n >= 65534)
+        return fail(SB_EINVAL, "sb_fast_tables_check: bad shape%s (M=%ld)", "", M);
+    int w = 1;
+    while (w < (M + 1 > n + 1 ? M + 1 : n + 1)) w <<= 1;
+    const int H = w / M, Hp = H < 16 ? 16 : H, logM = ilog2(M), SBQ = sign_bit(logM);
+    FastTables ft;
+    build_fast_tables(ordering, L, M, n, Hp, ft);
+    if (stats) { stats[0] = ft.fold_steps; stats[1] = ft.fold_wavefronts; stats[2] = ft.gather_steps; stats[3] = ft.gather_wavefronts; }
+    if (!ft.qok) return 1;
+    const int osh = ft.qpre ? 2 : 0;
+    std::vector<int> seen(n);
+    for (int l = 0; l < L; l++) {
+        std::fill(seen.begin(), seen.end(), 0);
+        for (int j = 0; j < M; j++)
+            for (int t = 0; t < Hp; t++) {
+                const int o = ft.invq[((size_t)l * M + j) * Hp + t] >> osh;
+                if (o >= n && o < n + 32) continue;  // zero word
+                const int neg = o >= ft.qneg, k = neg ? o - ft.qneg : o;
+                if (k < 0 || k >= n) return fail(SB_EINVAL, "fast tables: fold offset out of range%s (%ld)", "", o);
+                const uint32_t r = ordering[(size_t)l * n + k];
+                if ((int)(r % M) != j || (__builtin_popcount(r / M) & 1) != neg || seen[k]++)
+                    return fail(SB_EINVAL, "fast tables: wrong fold term%s (section %ld)", "", l);
+            }
+        for (int k = 0; k < n; k++) if (seen[k] != 1) return fail(SB_EINVAL, "fast tables: missing fold term%s (section %ld)", "", l);
+    }
+    for (int g = 0; g < ft.G16; g++)
+        for (int k = 0; k < n; k++) {
+            unsigned mask = 0;
+            for (int t = 0; t < 16; t++) {
+                const uint32_t off = ft.fwd16[((size_t)g * n + k) * 16 + t];
+                const uint32_t region = off / (2u << SBQ), in = off % (2u << SBQ);
+                const uint32_t sg = in >> SBQ, rest = in & ((1u << SBQ) - 1), slot = region * 8 + rest / ((uint32_t)M << 2);
+                const uint32_t lo = (rest % ((uint32_t)M << 2)) >> 2;
+                if (slot >= 16 || (off & 3)) return fail(SB_EINVAL, "fast tables: bad gather offset%s (%ld)", "", off);
+                const uint32_t r = ordering[(size_t)(g * 16 + slot) * n + k];
+                if (r % M != lo || (uint32_t)(__builtin_popcount(r / M) & 1) != sg)
+                    return fail(SB_EINVAL, "fast tables: wrong gather term%s (chunk %ld)", "", g);
+                mask |= 1u << slot;
+            }
+            if (mask != 0xFFFFu) return fail(SB_EINVAL, "fast tables: missing gather term%s (chunk %ld)", "", g);
+        }
+    return SB_OK;
 }
 
 static AmpArgs base_args(const sb_operator *op, const int *sections, const int *nsec) {
     AmpArgs a;
     memset(&a, 0, sizeof(a));
     a.fwd = op->fwd; a.fwd8 = op->fwd8; a.inv = op->inv; a.sections = sections; a.nsec = nsec;
+    a.invq = op->invq; a.fwd16 = op->fwd16; a.qneg = op->qneg;
     a.L = op->L; a.n = op->n; a.Hp = op->Hp; a.NB = op->NB;
     return a;
 }
@@ -143,7 +321,7 @@ extern "C" int sb_amp_batch(const sb_operator *op, const double *y, const double
         return fail(SB_EINVAL, "sb_amp_batch: null argument%s", "");
     if (mode != SB_AMP_STRICT && mode != SB_AMP_FAST) return fail(SB_EINVAL, "sb_amp_batch: unknown mode%s %ld", "", mode);
     if ((sections == nullptr) != (nsec == nullptr)) return fail(SB_EINVAL, "sb_amp_batch: sections and nsec go together%s", "");
-    if (mode == SB_AMP_FAST && op->pre && !scratch) return fail(SB_EINVAL, "sb_amp_batch: FAST mode needs a [B][n] scratch%s", "");
+    if (mode == SB_AMP_FAST && op->qok && !scratch) return fail(SB_EINVAL, "sb_amp_batch: FAST mode needs a [B][n] scratch%s", "");
     if (B == 0) return SB_OK;
     AmpArgs a = base_args(op, sections, nsec);
     a.zscratch = scratch;

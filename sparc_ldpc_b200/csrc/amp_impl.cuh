@@ -174,8 +174,50 @@ __device__ __forceinline__ void fold_section(double (&x)[TeamCfg<LOGM>::EPT], co
     }
 }
 
+// FAST mode: the bin's terms are signed fixed-point words (+z or -z copy, or a zero word) in an order chosen at
+// table-build time so that the lanes of a warp read distinct banks (sched.h); integer adds are order-free.
+template <bool PRE>
+__device__ __forceinline__ int fold16q(const uint4 p0, const uint4 p1, const int *zs) {
+    const uint32_t wds[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += zs_at<PRE, int>(zs, wds[i] & 0xFFFFu) + zs_at<PRE, int>(zs, wds[i] >> 16);
+    return s;
+}
+
+template <int LOGM, bool PRE>
+__device__ __forceinline__ void fold_section_q(double (&x)[TeamCfg<LOGM>::EPT], const uint16_t *__restrict__ tab,
+                                               int Hp, int NB, int q, const int *zs, double unit) {
+    constexpr int TEAM = TeamCfg<LOGM>::TEAM, EPT = TeamCfg<LOGM>::EPT;
+    if (NB == 1) {
+        const uint4 *t4 = reinterpret_cast<const uint4 *>(tab);  // Hp == 16: two uint4 per bin
+        uint4 c0 = __ldg(t4 + 2 * q), c1 = __ldg(t4 + 2 * q + 1);
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            uint4 n0 = c0, n1 = c1;
+            if (e + 1 < EPT) {
+                n0 = __ldg(t4 + 2 * ((e + 1) * TEAM + q));
+                n1 = __ldg(t4 + 2 * ((e + 1) * TEAM + q) + 1);
+            }
+            x[e] = (double)fold16q<PRE>(c0, c1, zs) * unit;
+            c0 = n0;
+            c1 = n1;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const uint4 *t4 = reinterpret_cast<const uint4 *>(tab + (size_t)(e * TEAM + q) * Hp);
+            double v = 0.0;
+            for (int c = 0; c < NB; c++) v += (double)fold16q<PRE>(__ldg(t4 + 2 * c), __ldg(t4 + 2 * c + 1), zs);
+            x[e] = v * unit;
+        }
+    }
+}
+
 struct AmpArgs {
     const uint16_t *fwd, *fwd8, *inv;
+    const uint16_t *invq, *fwd16;  // FAST mode: scheduled (bank-conflict-free) orderings of the same maps
+    int qneg;                      // word offset of the -z copy in the fixed-point z area
     const double *y, *Pl, *beta0;
     const int *sections, *nsec;
     double *beta, *tau2_trace, *zscratch;
@@ -199,11 +241,12 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
     double x[EPT];
     const unsigned tmask = team_mask<TEAM>();
     if (mode == 0) {
-        const uint16_t *tab = a.inv + ((size_t)sec * M) * a.Hp;
         if (QUANT)
-            fold_section<LOGM, PRE, int>(x, tab, a.Hp, a.NB, q, static_cast<const int *>(zsv), cx.zunit);
+            fold_section_q<LOGM, PRE>(x, a.invq + ((size_t)sec * M) * a.Hp, a.Hp, a.NB, q,
+                                      static_cast<const int *>(zsv), cx.zunit);
         else
-            fold_section<LOGM, PRE, double>(x, tab, a.Hp, a.NB, q, static_cast<const double *>(zsv), 1.0);
+            fold_section<LOGM, PRE, double>(x, a.inv + ((size_t)sec * M) * a.Hp, a.Hp, a.NB, q,
+                                            static_cast<const double *>(zsv), 1.0);
         fht_team<LOGM>(x, q, tmask);
         const double c2 = rt_npl / cx.tau2;
         double m = -INFINITY;
@@ -272,12 +315,12 @@ __device__ __forceinline__ T F_at(const char *slot_base, uint32_t e) {
 // every 16 sections so that the int32 partial sums cannot overflow).
 template <int LOGM, typename T>
 __device__ __forceinline__ void gather_phase(const uint16_t *__restrict__ fwd, int n, int nvalid, const int *sec_s,
-                                             const char *Fbytes, double *acc_s, double funit) {
+                                             const char *Fbytes, double *acc_s, double funit, int first = 0) {
     constexpr int ESH = sizeof(T) == 8 ? 3 : 2;
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
         double acc = acc_s[k];
         T part = 0;
-        int tm = 0;
+        int tm = first;
         for (; tm + 4 <= nvalid; tm += 4) {
             uint32_t e[4];
 #pragma unroll
@@ -287,7 +330,7 @@ __device__ __forceinline__ void gather_phase(const uint16_t *__restrict__ fwd, i
                 const T v = F_at<T>(Fbytes + slot_offset<LOGM, ESH>(tm + i), e[i]);
                 if (sizeof(T) == 8) acc += v; else part += v;
             }
-            if (sizeof(T) != 8 && ((tm + 4) & 15) == 0) {
+            if (sizeof(T) != 8 && ((tm + 4 - first) & 15) == 0) {
                 acc += (double)part * funit;
                 part = 0;
             }
@@ -380,6 +423,51 @@ __device__ __forceinline__ void gather_phase8(const uint16_t *__restrict__ fwd8,
     }
 }
 
+// FAST mode, all sections in order: the 16 entries of (16-section chunk, row k) are two 16-byte loads from the
+// scheduled table; every entry is the byte offset of its signed F word inside the chunk's +-F area, and the
+// order of the 16 entries differs from row to row such that the 32 rows of a warp read distinct banks.
+template <int LOGM>
+__device__ __forceinline__ void gather_phase16q(const uint16_t *__restrict__ fwd16, int n, int g0, int nchunks,
+                                                const char *Fbytes, double *acc_s, double funit) {
+    constexpr int KB = 3;
+    const uint4 *tab = reinterpret_cast<const uint4 *>(fwd16) + (size_t)(g0 >> 4) * n * 2;
+    const int NT = blockDim.x;
+    for (int k0 = threadIdx.x; k0 < n; k0 += KB * NT) {
+        double acc[KB];
+        int kk[KB];
+#pragma unroll
+        for (int j = 0; j < KB; j++) {
+            const int k = k0 + j * NT;
+            kk[j] = (k < n) ? k : k0;  // clamp: a duplicate row is gathered and then discarded
+            acc[j] = acc_s[kk[j]];
+        }
+        for (int c = 0; c < nchunks; c++) {
+            uint4 w0[KB], w1[KB];
+#pragma unroll
+            for (int j = 0; j < KB; j++) {
+                w0[j] = __ldg(tab + ((size_t)c * n + kk[j]) * 2);
+                w1[j] = __ldg(tab + ((size_t)c * n + kk[j]) * 2 + 1);
+            }
+            const char *F = Fbytes + slot_offset<LOGM, 2>(c * 16);
+#pragma unroll
+            for (int j = 0; j < KB; j++) {
+                const uint32_t wds[8] = {w0[j].x, w0[j].y, w0[j].z, w0[j].w, w1[j].x, w1[j].y, w1[j].z, w1[j].w};
+                int part = 0;  // 16 terms of < 2^27 each
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    part += *reinterpret_cast<const int *>(F + (wds[i] & 0xFFFFu)) +
+                            *reinterpret_cast<const int *>(F + (wds[i] >> 16));
+                acc[j] += (double)part * funit;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KB; j++) {
+            const int k = k0 + j * NT;
+            if (k < n) acc_s[k] = acc[j];
+        }
+    }
+}
+
 // One pass over all active sections: section_phase per team, then the gather per group.
 template <int LOGM, bool PRE, bool QUANT>
 __device__ __forceinline__ void operator_pass(int mode, bool first_zero, const AmpArgs &a, const double *bsrc,
@@ -406,7 +494,11 @@ __device__ __forceinline__ void operator_pass(int mode, bool first_zero, const A
         const bool fast = (act == nullptr && (W & 7) == 0);
         const double funit = 1.0 / cx.fscale;
         if (qpass) {
-            if (fast) gather_phase8<LOGM, int>(a.fwd8, a.n, g0, nvalid, Fbytes, acc_s, funit);
+            if (LOGM <= 9 && act == nullptr && a.fwd16 != nullptr && nvalid >= 16) {
+                const int nch = nvalid >> 4;  // complete 16-section chunks: scheduled table
+                gather_phase16q<LOGM>(a.fwd16, a.n, g0, nch, Fbytes, acc_s, funit);
+                if (nch * 16 < nvalid) gather_phase<LOGM, int>(a.fwd, a.n, nvalid, sec_s, Fbytes, acc_s, funit, nch * 16);
+            } else if (fast) gather_phase8<LOGM, int>(a.fwd8, a.n, g0, nvalid, Fbytes, acc_s, funit);
             else gather_phase<LOGM, int>(a.fwd, a.n, nvalid, sec_s, Fbytes, acc_s, funit);
         } else {
             if (fast) gather_phase8<LOGM, double>(a.fwd8, a.n, g0, nvalid, Fbytes, acc_s, 1.0);
@@ -417,8 +509,9 @@ __device__ __forceinline__ void operator_pass(int mode, bool first_zero, const A
 }
 
 // shared-memory carve-up.  strict: z fp64 [n+1 (zero word)] | acc | F (fp64 +-) | red | sec
-//                          quant : zq int32 [n+1 (zero word)] | acc | F (int32 +-) | red | sec   (fp64 z lives in a
-//                                  per-codeword global scratch row: it is only touched element-wise)
+//                          quant : zq int32 [+z (n) | 32 zero words | -z (n)] | acc | F (int32 +-) | red | sec
+//                                  (fp64 z lives in a per-codeword global scratch row: it is only touched
+//                                  element-wise)
 template <int LOGM, bool QUANT>
 struct Smem {
     double *zf, *acc, *red;
@@ -430,7 +523,7 @@ struct Smem {
         return (size_t)regions * ((QUANT ? 2 : 4) << TeamCfg<LOGM>::SBQ);
     }
     __host__ __device__ static size_t bytes(int n, int W) {
-        size_t b = QUANT ? sizeof(int) * (size_t)pad4(n + 1) : sizeof(double) * (size_t)pad2(n + 1);
+        size_t b = QUANT ? sizeof(int) * (size_t)pad4(2 * n + 32) : sizeof(double) * (size_t)pad2(n + 1);
         b += sizeof(double) * (size_t)pad2(n);  // acc
         b += f_bytes(W);
         b += sizeof(double) * 40 + sizeof(int) * (size_t)(W + 2);
@@ -440,7 +533,7 @@ struct Smem {
         if (QUANT) {
             zq = reinterpret_cast<int *>(raw);
             zf = nullptr;
-            acc = reinterpret_cast<double *>(zq + pad4(n + 1));
+            acc = reinterpret_cast<double *>(zq + pad4(2 * n + 32));
         } else {
             zq = nullptr;
             zf = reinterpret_cast<double *>(raw);
@@ -463,8 +556,10 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
     Smem<LOGM, QUANT> sm(smem_raw, n, W);
     double *zf = QUANT ? a.zscratch + (size_t)b * n : sm.zf;  // every thread only touches its own k = tid + j*NT
     double *acc_s = sm.acc, *red = sm.red;
-    if (threadIdx.x == 0) {
-        if (QUANT) sm.zq[n] = 0; else zf[n] = 0.0;
+    if (QUANT) {
+        if (threadIdx.x < 32) sm.zq[n + threadIdx.x] = 0;  // one zero word per bank
+    } else if (threadIdx.x == 0) {
+        zf[n] = 0.0;
     }
     const void *zsv = QUANT ? static_cast<const void *>(sm.zq) : static_cast<const void *>(zf);
 
@@ -552,7 +647,11 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
             const double zscale = scalbn(1.0, 27 - ez);
             cx.zunit = scalbn(1.0, ez - 27);
             cx.fscale = fscale_q;
-            for (int k = threadIdx.x; k < n; k += blockDim.x) sm.zq[k] = __double2int_rn(zf[k] * zscale);
+            for (int k = threadIdx.x; k < n; k += blockDim.x) {
+                const int v = __double2int_rn(zf[k] * zscale);
+                sm.zq[k] = v;
+                sm.zq[a.qneg + k] = -v;
+            }
             __syncthreads();
         }
         sq = 0.0;
@@ -630,7 +729,7 @@ template <int LOGM, bool QUANT>
 static int pick_threads(int n, int L, size_t *smem_out, int *W_out) {
     constexpr int TEAM = TeamCfg<LOGM>::TEAM;
     int nt = 512;
-    if (QUANT && TEAM == 32 && 2 * (Smem<LOGM, QUANT>::bytes(n, 256 / TEAM) + 1024) <= 227 * 1024) nt = 256;
+    if (QUANT && LOGM > 9 && TEAM == 32 && 2 * (Smem<LOGM, QUANT>::bytes(n, 256 / TEAM) + 1024) <= 227 * 1024) nt = 256;
     const char *env = getenv("SB_AMP_THREADS");
     if (env) nt = atoi(env);
     if (nt > 512) nt = 512;
@@ -649,7 +748,7 @@ template <int LOGM>
 int launch_amp(const sb_operator *op, AmpArgs a, int B, int which, const double *in, double *out, cudaStream_t st) {
     size_t smem = 0;
     int W = 0;
-    const bool quant = (which == 3) && op->pre;
+    const bool quant = (which == 3) && op->qok;
     const int nt = quant ? pick_threads<LOGM, true>(op->n, op->L, &smem, &W)
                          : pick_threads<LOGM, false>(op->n, op->L, &smem, &W);
     if (smem > 227 * 1024) return fail(SB_EINVAL, "AMP: n too large for shared memory%s (%ld bytes)", "", (long)smem);
@@ -659,7 +758,8 @@ int launch_amp(const sb_operator *op, AmpArgs a, int B, int which, const double 
         KERNEL<<<B, nt, smem, st>>>(__VA_ARGS__);                                                        \
     } while (0)
     if (which == 0 || which == 3) {
-        if (quant) SB_LAUNCH((amp_kernel<LOGM, true, true>), a, W);
+        if (quant && op->qpre) SB_LAUNCH((amp_kernel<LOGM, true, true>), a, W);
+        else if (quant) SB_LAUNCH((amp_kernel<LOGM, false, true>), a, W);
         else if (op->pre) SB_LAUNCH((amp_kernel<LOGM, true, false>), a, W);
         else SB_LAUNCH((amp_kernel<LOGM, false, false>), a, W);
     } else if (which == 1) {
