@@ -78,8 +78,8 @@ static int sign_bit(int logM) { return logM + 2 + (logM >= 10 ? 2 : 3); }
 // ---- FAST-mode tables: conflict-free orderings of the two shared-memory gathers (sched.h) -------------------
 // Host-only; sb_operator_create uploads the result, sb_fast_tables_check (tests) verifies it without a GPU.
 struct FastTables {
-    int qok = 0, qpre = 0, qneg = 0, G16 = 0;
-    std::vector<uint16_t> invq, fwd16;
+    int qok = 0, qpre = 0, qneg = 0, PW = 0, GQ = 0;  // PW = sections per gather pool (8 | 16), GQ = floor(L / PW)
+    std::vector<uint16_t> invq, fwdq;
     long fold_steps = 0, fold_wavefronts = 0, gather_steps = 0, gather_wavefronts = 0;  // bank-conflict model
 };
 
@@ -99,8 +99,18 @@ static void parallel_for(int count, const std::function<void(int, int)> &body) {
     for (auto &x : th) x.join();
 }
 
+// shared memory of the FAST kernel with W section slots (= Smem<LOGM, true>::bytes, logM <= 9)
+static size_t fast_smem_bytes(int logM, int n, int W) {
+    const size_t region = (size_t)2 << sign_bit(logM);
+    return 4 * (size_t)pad4(2 * n + 32) + 8 * (size_t)pad2(n) + (size_t)((W + 7) / 8) * region + 8 * 40 + 4 * (size_t)(W + 2);
+}
+
+// Table layouts (16-bit entries, every lane reads 16 bytes = 8 entries per load and the 32 lanes of a warp read
+// 512 contiguous bytes):
+//   invq [L][EPT][Hp/8][TEAM][8]   entry t = h*8+i of bin e*TEAM+q: offset into [ +z | 32 zero words | -z ]
+//   fwdq [GQ][PW/8][n][8]          entry t = h*8+i of (chunk, row k): byte offset into the chunk's +-F area
 static void build_fast_tables(const uint32_t *ordering, int L, int M, int n, int Hp, FastTables &ft) {
-    const int logM = ilog2(M), SBQ = sign_bit(logM), TEAM = team_lanes(M), EPT = M / TEAM;
+    const int logM = ilog2(M), SBQ = sign_bit(logM), TEAM = team_lanes(M), EPT = M / TEAM, NH = Hp / 8;
     ft.qneg = n + 32;
     if (2L * n + 32 > 65535) return;  // offsets do not fit 16 bits: FAST falls back to STRICT
     ft.qok = 1;
@@ -137,22 +147,30 @@ static void build_fast_tables(const uint32_t *ordering, int L, int M, int n, int
                     for (int b = 0; b < 32; b++) if (!used[(size_t)t * 32 + b]) { fb = b; break; }
                     const int zero_word = n + ((fb - n) & 31);  // word in [n, n+32) with bank fb
                     for (int q = 0; q < TEAM; q++)
-                        ft.invq[((size_t)l * M + e * TEAM + q) * Hp + t] = (uint16_t)(zero_word << osh);
+                        ft.invq[((((size_t)l * EPT + e) * NH + (t >> 3)) * TEAM + q) * 8 + (t & 7)] = (uint16_t)(zero_word << osh);
                 }
                 for (const PoolEdge &pe : E)
-                    ft.invq[((size_t)l * M + e * TEAM + pe.lane) * Hp + pe.step] = (uint16_t)(pe.id << osh);
+                    ft.invq[((((size_t)l * EPT + e) * NH + (pe.step >> 3)) * TEAM + pe.lane) * 8 + (pe.step & 7)] =
+                        (uint16_t)(pe.id << osh);
             }
         }
     });
     for (int l = 0; l < L; l++) { ft.fold_steps += stat[(size_t)l * 2]; ft.fold_wavefronts += stat[(size_t)l * 2 + 1]; }
-    // gather: pool = (chunk of 16 sections, warp row of 32 consecutive k); lane k%32 reads one section per step
+    // gather: pool = (chunk of PW sections, warp row of 32 consecutive k); lane k%32 reads one section per step.
+    // PW = 16 (one 512-thread CTA per SM, 1.75 wavefronts per step) measured faster than PW = 8 (two 256-thread
+    // CTAs per SM, 2.0 wavefronts per step): 3.49 vs 3.68 us per codeword-iteration at L=M=512.  SB_AMP_POOL=8
+    // selects the latter for experiments when two CTAs fit.
     if (logM > 9) return;
-    ft.G16 = L / 16;
-    if (ft.G16 == 0) return;
-    ft.fwd16.assign((size_t)ft.G16 * n * 16, 0);
+    ft.PW = 16;
+    if (const char *env = getenv("SB_AMP_POOL"))
+        if (atoi(env) == 8 && TEAM == 32 && 2 * (fast_smem_bytes(logM, n, 8) + 1024) <= 227 * 1024) ft.PW = 8;
+    const int PW = ft.PW;
+    ft.GQ = L / PW;
+    if (ft.GQ == 0) return;
+    ft.fwdq.assign((size_t)ft.GQ * n * PW, 0);
     const int SPR = 8;
-    std::vector<long> gstat((size_t)ft.G16 * 2, 0);
-    parallel_for(ft.G16, [&](int g0, int g1) {
+    std::vector<long> gstat((size_t)ft.GQ * 2, 0);
+    parallel_for(ft.GQ, [&](int g0, int g1) {
         PoolScheduler ps;
         std::vector<PoolEdge> E;
         for (int g = g0; g < g1; g++)
@@ -160,22 +178,22 @@ static void build_fast_tables(const uint32_t *ordering, int L, int M, int n, int
                 E.clear();
                 const int nl = (n - k0 < 32) ? n - k0 : 32;
                 for (int q = 0; q < nl; q++)
-                    for (int i = 0; i < 16; i++) {
-                        const uint32_t r = ordering[(size_t)(g * 16 + i) * n + k0 + q];
+                    for (int i = 0; i < PW; i++) {
+                        const uint32_t r = ordering[(size_t)(g * PW + i) * n + k0 + q];
                         const uint32_t lo = r % M, sg = __builtin_popcount(r / M) & 1;
                         const uint32_t off = (uint32_t)(i / SPR) * (2u << SBQ) + (uint32_t)(i % SPR) * ((uint32_t)M << 2) +
                                              (lo << 2) + (sg << SBQ);
                         E.push_back(PoolEdge{q, (int)((off >> 2) & 31), (int)off, 0});
                     }
-                ps.run(E, 16);
-                PoolScheduler::improve(E, 16);
-                gstat[(size_t)g * 2] += 16;
-                gstat[(size_t)g * 2 + 1] += PoolScheduler::cost(E, 16);
+                ps.run(E, PW);
+                PoolScheduler::improve(E, PW);
+                gstat[(size_t)g * 2] += PW;
+                gstat[(size_t)g * 2 + 1] += PoolScheduler::cost(E, PW);
                 for (const PoolEdge &pe : E)
-                    ft.fwd16[((size_t)g * n + k0 + pe.lane) * 16 + pe.step] = (uint16_t)pe.id;
+                    ft.fwdq[(((size_t)g * (PW / 8) + (pe.step >> 3)) * n + k0 + pe.lane) * 8 + (pe.step & 7)] = (uint16_t)pe.id;
             }
     });
-    for (int g = 0; g < ft.G16; g++) { ft.gather_steps += gstat[(size_t)g * 2]; ft.gather_wavefronts += gstat[(size_t)g * 2 + 1]; }
+    for (int g = 0; g < ft.GQ; g++) { ft.gather_steps += gstat[(size_t)g * 2]; ft.gather_wavefronts += gstat[(size_t)g * 2 + 1]; }
 }
 
 }  // namespace sb
@@ -213,27 +231,27 @@ extern "C" int sb_operator_create(const uint32_t *ordering, int L, int M, int n,
             h8[((size_t)(l >> 3) * n + k) * 8 + (l & 7)] = fe;
             hi[((size_t)l * M + lo) * op->Hp + c] = (uint16_t)(op->pre ? k * 4 : k);
         }
-    op->fwd = nullptr; op->inv = nullptr; op->fwd8 = nullptr; op->invq = nullptr; op->fwd16 = nullptr;
+    op->fwd = nullptr; op->inv = nullptr; op->fwd8 = nullptr; op->invq = nullptr; op->fwdq = nullptr;
     {   // FAST-mode tables (scheduled gathers)
         FastTables ft;
         build_fast_tables(ordering, L, M, n, op->Hp, ft);
-        op->qok = ft.qok; op->qpre = ft.qpre; op->qneg = ft.qneg; op->G16 = ft.G16;
+        op->qok = ft.qok; op->qpre = ft.qpre; op->qneg = ft.qneg; op->PW = ft.PW; op->GQ = ft.GQ;
         if (ft.qok) {
             cudaError_t q1 = cudaMalloc(&op->invq, ft.invq.size() * 2), q2 = cudaSuccess;
             if (q1 == cudaSuccess) q1 = cudaMemcpy(op->invq, ft.invq.data(), ft.invq.size() * 2, cudaMemcpyHostToDevice);
-            if (ft.G16 > 0) {
-                q2 = cudaMalloc(&op->fwd16, ft.fwd16.size() * 2);
-                if (q2 == cudaSuccess) q2 = cudaMemcpy(op->fwd16, ft.fwd16.data(), ft.fwd16.size() * 2, cudaMemcpyHostToDevice);
+            if (ft.GQ > 0) {
+                q2 = cudaMalloc(&op->fwdq, ft.fwdq.size() * 2);
+                if (q2 == cudaSuccess) q2 = cudaMemcpy(op->fwdq, ft.fwdq.data(), ft.fwdq.size() * 2, cudaMemcpyHostToDevice);
             }
             if (q1 != cudaSuccess || q2 != cudaSuccess) {
-                cudaFree(op->invq); cudaFree(op->fwd16); free(hf); free(hi); free(h8); delete op;
+                cudaFree(op->invq); cudaFree(op->fwdq); free(hf); free(hi); free(h8); delete op;
                 return fail(SB_ENOMEM, "sb_operator_create: cudaMalloc (fast tables) failed%s", "");
             }
         }
     }
     cudaError_t e1 = cudaMalloc(&op->fwd, nf * 2), e2 = cudaMalloc(&op->inv, ni * 2), e3 = cudaMalloc(&op->fwd8, n8 * 2);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-        cudaFree(op->fwd); cudaFree(op->inv); cudaFree(op->fwd8); cudaFree(op->invq); cudaFree(op->fwd16);
+        cudaFree(op->fwd); cudaFree(op->inv); cudaFree(op->fwd8); cudaFree(op->invq); cudaFree(op->fwdq);
         free(hf); free(hi); free(h8); delete op;
         return fail(SB_ENOMEM, "sb_operator_create: cudaMalloc failed%s", "");
     }
@@ -252,7 +270,7 @@ extern "C" void sb_operator_destroy(sb_operator *op) {
     cudaFree(op->fwd8);
     cudaFree(op->inv);
     cudaFree(op->invq);
-    cudaFree(op->fwd16);
+    cudaFree(op->fwdq);
     delete op;
 }
 
@@ -270,13 +288,13 @@ extern "C" int sb_fast_tables_check(const uint32_t *ordering, int L, int M, int 
     build_fast_tables(ordering, L, M, n, Hp, ft);
     if (stats) { stats[0] = ft.fold_steps; stats[1] = ft.fold_wavefronts; stats[2] = ft.gather_steps; stats[3] = ft.gather_wavefronts; }
     if (!ft.qok) return 1;
-    const int osh = ft.qpre ? 2 : 0;
+    const int osh = ft.qpre ? 2 : 0, TEAM = team_lanes(M), EPT = M / TEAM, NH = Hp / 8, PW = ft.PW;
     std::vector<int> seen(n);
     for (int l = 0; l < L; l++) {
         std::fill(seen.begin(), seen.end(), 0);
         for (int j = 0; j < M; j++)
             for (int t = 0; t < Hp; t++) {
-                const int o = ft.invq[((size_t)l * M + j) * Hp + t] >> osh;
+                const int o = ft.invq[((((size_t)l * EPT + j / TEAM) * NH + (t >> 3)) * TEAM + j % TEAM) * 8 + (t & 7)] >> osh;
                 if (o >= n && o < n + 32) continue;  // zero word
                 const int neg = o >= ft.qneg, k = neg ? o - ft.qneg : o;
                 if (k < 0 || k >= n) return fail(SB_EINVAL, "fast tables: fold offset out of range%s (%ld)", "", o);
@@ -286,21 +304,21 @@ extern "C" int sb_fast_tables_check(const uint32_t *ordering, int L, int M, int 
             }
         for (int k = 0; k < n; k++) if (seen[k] != 1) return fail(SB_EINVAL, "fast tables: missing fold term%s (section %ld)", "", l);
     }
-    for (int g = 0; g < ft.G16; g++)
+    for (int g = 0; g < ft.GQ; g++)
         for (int k = 0; k < n; k++) {
             unsigned mask = 0;
-            for (int t = 0; t < 16; t++) {
-                const uint32_t off = ft.fwd16[((size_t)g * n + k) * 16 + t];
+            for (int t = 0; t < PW; t++) {
+                const uint32_t off = ft.fwdq[(((size_t)g * (PW / 8) + (t >> 3)) * n + k) * 8 + (t & 7)];
                 const uint32_t region = off / (2u << SBQ), in = off % (2u << SBQ);
                 const uint32_t sg = in >> SBQ, rest = in & ((1u << SBQ) - 1), slot = region * 8 + rest / ((uint32_t)M << 2);
                 const uint32_t lo = (rest % ((uint32_t)M << 2)) >> 2;
-                if (slot >= 16 || (off & 3)) return fail(SB_EINVAL, "fast tables: bad gather offset%s (%ld)", "", off);
-                const uint32_t r = ordering[(size_t)(g * 16 + slot) * n + k];
+                if (slot >= (uint32_t)PW || (off & 3)) return fail(SB_EINVAL, "fast tables: bad gather offset%s (%ld)", "", off);
+                const uint32_t r = ordering[(size_t)(g * PW + slot) * n + k];
                 if (r % M != lo || (uint32_t)(__builtin_popcount(r / M) & 1) != sg)
                     return fail(SB_EINVAL, "fast tables: wrong gather term%s (chunk %ld)", "", g);
                 mask |= 1u << slot;
             }
-            if (mask != 0xFFFFu) return fail(SB_EINVAL, "fast tables: missing gather term%s (chunk %ld)", "", g);
+            if (mask != (PW == 16 ? 0xFFFFu : 0xFFu)) return fail(SB_EINVAL, "fast tables: missing gather term%s (chunk %ld)", "", g);
         }
     return SB_OK;
 }
@@ -309,7 +327,7 @@ static AmpArgs base_args(const sb_operator *op, const int *sections, const int *
     AmpArgs a;
     memset(&a, 0, sizeof(a));
     a.fwd = op->fwd; a.fwd8 = op->fwd8; a.inv = op->inv; a.sections = sections; a.nsec = nsec;
-    a.invq = op->invq; a.fwd16 = op->fwd16; a.qneg = op->qneg;
+    a.invq = op->invq; a.fwdq = op->fwdq; a.qneg = op->qneg; a.PW = op->PW;
     a.L = op->L; a.n = op->n; a.Hp = op->Hp; a.NB = op->NB;
     return a;
 }

@@ -185,19 +185,21 @@ __device__ __forceinline__ int fold16q(const uint4 p0, const uint4 p1, const int
     return s;
 }
 
+// table of one section: [EPT][2*NB][TEAM][8 entries]; the two (2*NB) 16-byte loads of bin e+1 are issued before
+// bin e is reduced when NB == 1 (w/M <= 16, the headline shapes)
 template <int LOGM, bool PRE>
 __device__ __forceinline__ void fold_section_q(double (&x)[TeamCfg<LOGM>::EPT], const uint16_t *__restrict__ tab,
-                                               int Hp, int NB, int q, const int *zs, double unit) {
+                                               int NB, int q, const int *zs, double unit) {
     constexpr int TEAM = TeamCfg<LOGM>::TEAM, EPT = TeamCfg<LOGM>::EPT;
+    const uint4 *t4 = reinterpret_cast<const uint4 *>(tab) + q;
     if (NB == 1) {
-        const uint4 *t4 = reinterpret_cast<const uint4 *>(tab);  // Hp == 16: two uint4 per bin
-        uint4 c0 = __ldg(t4 + 2 * q), c1 = __ldg(t4 + 2 * q + 1);
+        uint4 c0 = __ldg(t4), c1 = __ldg(t4 + TEAM);
 #pragma unroll
         for (int e = 0; e < EPT; e++) {
             uint4 n0 = c0, n1 = c1;
             if (e + 1 < EPT) {
-                n0 = __ldg(t4 + 2 * ((e + 1) * TEAM + q));
-                n1 = __ldg(t4 + 2 * ((e + 1) * TEAM + q) + 1);
+                n0 = __ldg(t4 + (2 * (e + 1)) * TEAM);
+                n1 = __ldg(t4 + (2 * (e + 1) + 1) * TEAM);
             }
             x[e] = (double)fold16q<PRE>(c0, c1, zs) * unit;
             c0 = n0;
@@ -206,9 +208,10 @@ __device__ __forceinline__ void fold_section_q(double (&x)[TeamCfg<LOGM>::EPT], 
     } else {
 #pragma unroll
         for (int e = 0; e < EPT; e++) {
-            const uint4 *t4 = reinterpret_cast<const uint4 *>(tab + (size_t)(e * TEAM + q) * Hp);
+            const uint4 *te = t4 + (size_t)e * 2 * NB * TEAM;
             double v = 0.0;
-            for (int c = 0; c < NB; c++) v += (double)fold16q<PRE>(__ldg(t4 + 2 * c), __ldg(t4 + 2 * c + 1), zs);
+            for (int c = 0; c < NB; c++)
+                v += (double)fold16q<PRE>(__ldg(te + (2 * c) * TEAM), __ldg(te + (2 * c + 1) * TEAM), zs);
             x[e] = v * unit;
         }
     }
@@ -216,8 +219,9 @@ __device__ __forceinline__ void fold_section_q(double (&x)[TeamCfg<LOGM>::EPT], 
 
 struct AmpArgs {
     const uint16_t *fwd, *fwd8, *inv;
-    const uint16_t *invq, *fwd16;  // FAST mode: scheduled (bank-conflict-free) orderings of the same maps
-    int qneg;                      // word offset of the -z copy in the fixed-point z area
+    const uint16_t *invq, *fwdq;  // FAST mode: scheduled (bank-conflict-free) orderings of the same maps
+    int qneg;                     // word offset of the -z copy in the fixed-point z area
+    int PW;                       // sections per scheduled gather chunk (8 | 16)
     const double *y, *Pl, *beta0;
     const int *sections, *nsec;
     double *beta, *tau2_trace, *zscratch;
@@ -242,8 +246,8 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
     const unsigned tmask = team_mask<TEAM>();
     if (mode == 0) {
         if (QUANT)
-            fold_section_q<LOGM, PRE>(x, a.invq + ((size_t)sec * M) * a.Hp, a.Hp, a.NB, q,
-                                      static_cast<const int *>(zsv), cx.zunit);
+            fold_section_q<LOGM, PRE>(x, a.invq + ((size_t)sec * M) * a.Hp, a.NB, q, static_cast<const int *>(zsv),
+                                      cx.zunit);
         else
             fold_section<LOGM, PRE, double>(x, a.inv + ((size_t)sec * M) * a.Hp, a.Hp, a.NB, q,
                                             static_cast<const double *>(zsv), 1.0);
@@ -423,14 +427,15 @@ __device__ __forceinline__ void gather_phase8(const uint16_t *__restrict__ fwd8,
     }
 }
 
-// FAST mode, all sections in order: the 16 entries of (16-section chunk, row k) are two 16-byte loads from the
-// scheduled table; every entry is the byte offset of its signed F word inside the chunk's +-F area, and the
-// order of the 16 entries differs from row to row such that the 32 rows of a warp read distinct banks.
-template <int LOGM>
-__device__ __forceinline__ void gather_phase16q(const uint16_t *__restrict__ fwd16, int n, int g0, int nchunks,
-                                                const char *Fbytes, double *acc_s, double funit) {
-    constexpr int KB = 3;
-    const uint4 *tab = reinterpret_cast<const uint4 *>(fwd16) + (size_t)(g0 >> 4) * n * 2;
+// FAST mode, all sections in order: the PW entries of (PW-section chunk, row k) are PW/8 16-byte loads from the
+// scheduled table [chunk][PW/8][n][8]; every entry is the byte offset of its signed F word inside the chunk's
+// +-F area, and the order of the entries differs from row to row such that the 32 rows of a warp read distinct
+// banks (sched.h).
+template <int LOGM, int PW>
+__device__ __forceinline__ void gather_phaseq(const uint16_t *__restrict__ fwdq, int n, int g0, int nchunks,
+                                              const char *Fbytes, double *acc_s, double funit) {
+    constexpr int KB = 3, NH = PW / 8;
+    const uint4 *tab = reinterpret_cast<const uint4 *>(fwdq) + (size_t)(g0 / PW) * NH * n;
     const int NT = blockDim.x;
     for (int k0 = threadIdx.x; k0 < n; k0 += KB * NT) {
         double acc[KB];
@@ -441,22 +446,33 @@ __device__ __forceinline__ void gather_phase16q(const uint16_t *__restrict__ fwd
             kk[j] = (k < n) ? k : k0;  // clamp: a duplicate row is gathered and then discarded
             acc[j] = acc_s[kk[j]];
         }
-        for (int c = 0; c < nchunks; c++) {
-            uint4 w0[KB], w1[KB];
+        for (int c = 0; c < nchunks; c += 16 / PW) {  // <= 16 terms of < 2^27 each per int32 partial sum
+            uint4 w[16 / PW][NH][KB];
+#pragma unroll
+            for (int cc = 0; cc < 16 / PW; cc++)
+#pragma unroll
+                for (int h = 0; h < NH; h++)
+#pragma unroll
+                    for (int j = 0; j < KB; j++)
+                        w[cc][h][j] = (c + cc < nchunks) ? __ldg(tab + ((size_t)(c + cc) * NH + h) * n + kk[j])
+                                                         : make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int j = 0; j < KB; j++) {
-                w0[j] = __ldg(tab + ((size_t)c * n + kk[j]) * 2);
-                w1[j] = __ldg(tab + ((size_t)c * n + kk[j]) * 2 + 1);
-            }
-            const char *F = Fbytes + slot_offset<LOGM, 2>(c * 16);
+                int part = 0;
 #pragma unroll
-            for (int j = 0; j < KB; j++) {
-                const uint32_t wds[8] = {w0[j].x, w0[j].y, w0[j].z, w0[j].w, w1[j].x, w1[j].y, w1[j].z, w1[j].w};
-                int part = 0;  // 16 terms of < 2^27 each
+                for (int cc = 0; cc < 16 / PW; cc++) {
+                    if (c + cc < nchunks) {
+                        const char *F = Fbytes + slot_offset<LOGM, 2>((c + cc) * PW);
 #pragma unroll
-                for (int i = 0; i < 8; i++)
-                    part += *reinterpret_cast<const int *>(F + (wds[i] & 0xFFFFu)) +
-                            *reinterpret_cast<const int *>(F + (wds[i] >> 16));
+                        for (int h = 0; h < NH; h++) {
+                            const uint32_t wds[4] = {w[cc][h][j].x, w[cc][h][j].y, w[cc][h][j].z, w[cc][h][j].w};
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                part += *reinterpret_cast<const int *>(F + (wds[i] & 0xFFFFu)) +
+                                        *reinterpret_cast<const int *>(F + (wds[i] >> 16));
+                        }
+                    }
+                }
                 acc[j] += (double)part * funit;
             }
         }
@@ -494,10 +510,12 @@ __device__ __forceinline__ void operator_pass(int mode, bool first_zero, const A
         const bool fast = (act == nullptr && (W & 7) == 0);
         const double funit = 1.0 / cx.fscale;
         if (qpass) {
-            if (LOGM <= 9 && act == nullptr && a.fwd16 != nullptr && nvalid >= 16) {
-                const int nch = nvalid >> 4;  // complete 16-section chunks: scheduled table
-                gather_phase16q<LOGM>(a.fwd16, a.n, g0, nch, Fbytes, acc_s, funit);
-                if (nch * 16 < nvalid) gather_phase<LOGM, int>(a.fwd, a.n, nvalid, sec_s, Fbytes, acc_s, funit, nch * 16);
+            if (LOGM <= 9 && act == nullptr && a.fwdq != nullptr && nvalid >= a.PW && W % a.PW == 0) {
+                const int nch = nvalid / a.PW;  // complete chunks: scheduled table
+                if (a.PW == 8) gather_phaseq<LOGM, 8>(a.fwdq, a.n, g0, nch, Fbytes, acc_s, funit);
+                else gather_phaseq<LOGM, 16>(a.fwdq, a.n, g0, nch, Fbytes, acc_s, funit);
+                if (nch * a.PW < nvalid)
+                    gather_phase<LOGM, int>(a.fwd, a.n, nvalid, sec_s, Fbytes, acc_s, funit, nch * a.PW);
             } else if (fast) gather_phase8<LOGM, int>(a.fwd8, a.n, g0, nvalid, Fbytes, acc_s, funit);
             else gather_phase<LOGM, int>(a.fwd, a.n, nvalid, sec_s, Fbytes, acc_s, funit);
         } else {
@@ -726,10 +744,13 @@ __global__ void __launch_bounds__(512, 1) Az_kernel(AmpArgs a, int W, const doub
 // 256-thread CTAs per SM, whose gather (shared-memory pipe) and transform (fp64 / issue) phases then overlap.
 // Never more teams than sections, never more shared memory than 227 KB.
 template <int LOGM, bool QUANT>
-static int pick_threads(int n, int L, size_t *smem_out, int *W_out) {
+static int pick_threads(int n, int L, int pw, size_t *smem_out, int *W_out) {
     constexpr int TEAM = TeamCfg<LOGM>::TEAM;
     int nt = 512;
-    if (QUANT && LOGM > 9 && TEAM == 32 && 2 * (Smem<LOGM, QUANT>::bytes(n, 256 / TEAM) + 1024) <= 227 * 1024) nt = 256;
+    // FAST: two 256-thread CTAs per SM when the operator's gather table was built for 8-section chunks (or, for
+    // M = 1024, which has no scheduled gather table, whenever two CTAs fit)
+    if (QUANT && TEAM == 32 && (pw == 8 || (LOGM > 9 && 2 * (Smem<LOGM, QUANT>::bytes(n, 256 / TEAM) + 1024) <= 227 * 1024)))
+        nt = 256;
     const char *env = getenv("SB_AMP_THREADS");
     if (env) nt = atoi(env);
     if (nt > 512) nt = 512;
@@ -749,8 +770,8 @@ int launch_amp(const sb_operator *op, AmpArgs a, int B, int which, const double 
     size_t smem = 0;
     int W = 0;
     const bool quant = (which == 3) && op->qok;
-    const int nt = quant ? pick_threads<LOGM, true>(op->n, op->L, &smem, &W)
-                         : pick_threads<LOGM, false>(op->n, op->L, &smem, &W);
+    const int nt = quant ? pick_threads<LOGM, true>(op->n, op->L, op->PW, &smem, &W)
+                         : pick_threads<LOGM, false>(op->n, op->L, 0, &smem, &W);
     if (smem > 227 * 1024) return fail(SB_EINVAL, "AMP: n too large for shared memory%s (%ld bytes)", "", (long)smem);
 #define SB_LAUNCH(KERNEL, ...)                                                                           \
     do {                                                                                                 \

@@ -82,9 +82,10 @@ struct sb_operator {
     uint16_t *inv;                    // [L][M][Hp]  k (or k*8) / n (or n*8) = the zero word, visit order (A^T z fold)
     // FAST mode (fixed-point gathers): the same two maps with the order of every lane's terms chosen so that the
     // 32 lanes of a warp read distinct shared-memory banks (sched.h)
-    int qok, qpre, qneg, G16;  // qok: tables usable; qpre: invq holds byte offsets; qneg: word offset of the -z copy
-    uint16_t *invq;            // [L][M][Hp]   word (or byte) offset into [ +z (n) | 32 zero words | -z (n) ]
-    uint16_t *fwd16;           // [G16][n][16] byte offset into the +-F area of a 16-section chunk (logM <= 9)
+    int qok, qpre, qneg;  // qok: tables usable; qpre: invq holds byte offsets; qneg: word offset of the -z copy
+    int PW, GQ;           // gather pool = PW (8 | 16) sections; GQ = floor(L / PW) chunks in fwdq
+    uint16_t *invq;       // [L][EPT][Hp/8][TEAM][8]  word (or byte) offset into [ +z (n) | 32 zero words | -z (n) ]
+    uint16_t *fwdq;       // [GQ][PW/8][n][8]         byte offset into the +-F area of a PW-section chunk (logM <= 9)
 };
 
 struct sb_graph {
