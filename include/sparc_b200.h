@@ -152,6 +152,23 @@ int sb_bp2sp_prior_batch(const double *in, int ls, const double *beta_prev, int 
 int sb_section_softmax_batch(const double *s, const double *Pl, const double *tau2, const unsigned char *active, int L,
                              int M, int n, int B, double *beta, double *sumsq, void *stream);
 
+/* ------------------------------------------------------------------ (2c) dense (Gaussian) design matrix
+ * amp() of sparc_ldpc.py:189-222 with Ab = A @ beta, Az = A.T @ z for an explicit matrix A [n][L*M] (the
+ * reference takes the operator as two closures, :189; BASELINE configs[0]).  Both products run as hand-written
+ * tcgen05 / TMA GEMMs over the batch with a bf16x3 split of every operand (FP32 emulation: operands carried to
+ * 2^-27, six bf16 MMA passes, fp32 TMEM accumulation over at most 1024 values of k, fp64 across chunks); the
+ * AMP state (beta, z, tau^2, softmax, Onsager term) stays fp64.  A_dev: DEVICE pointer, row-major fp64. */
+typedef struct sb_dense sb_dense;
+int sb_dense_create(const double *A_dev, int n, int LM, sb_dense **out);
+void sb_dense_destroy(sb_dense *d);
+/* out[b] = A x[b]  (transpose = 0: x [B][LM] -> out [B][n])  or  A^T x[b]  (transpose = 1: x [B][n] -> out [B][LM]) */
+int sb_dense_apply_batch(sb_dense *d, int transpose, const double *x, int B, double *out, void *stream);
+/* Batched AMP decode; device pointers: y [B][n], Pl [L], beta0 [B][L*M] or NULL, beta [B][L*M] out,
+ * iters / n_exec / flags [B] out (as sb_amp_batch), tau2_trace [B][T] or NULL (NaN where not executed).
+ * Stop rule: tau == last_tau (sparc_ldpc.py:204) or |tau - last_tau| <= 2^-27 tau. */
+int sb_dense_amp_batch(sb_dense *d, const double *y, const double *Pl, const double *beta0, int L, int M, int B, int T,
+                       double *beta, int *iters, int *n_exec, unsigned *flags, double *tau2_trace, void *stream);
+
 /* idx[b][i] = argmax of section i of beta[b] (first maximum wins, sparc_ldpc.py:640-643) */
 int sb_argmax_batch(const double *beta, long beta_stride, int count, int M, int B, int *idx, long idx_stride,
                     void *stream);

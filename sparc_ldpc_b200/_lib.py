@@ -44,6 +44,10 @@ SIGNATURES = {
     "sb_sp2bp_llr_batch": (_i, [_vp, _l, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _l, _vp]),
     "sb_bp2sp_prior_batch": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "sb_section_softmax_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sb_dense_create": (_i, [_vp, _i, _i, ct.POINTER(_vp)]),
+    "sb_dense_destroy": (None, [_vp]),
+    "sb_dense_apply_batch": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "sb_dense_amp_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_argmax_batch": (_i, [_vp, _l, _i, _i, _i, _vp, _l, _vp]),
     "sb_llr2idx_batch": (_i, [_vp, _l, _i, _i, _i, _vp, _l, _vp]),
     "sb_count_errors_batch": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

@@ -1,0 +1,665 @@
+// dense.cu -- Gaussian (dense) design-matrix mode of the AMP decoder: A beta and A^T z as tcgen05 / TMA GEMMs.
+//
+// The reference's amp() takes the design operator as two closures (ldpc/sparc_ldpc.py:189, :213, :220); with a
+// dense i.i.d. Gaussian A (BASELINE configs[0]) they are s = beta + A^T z and A beta for every codeword of the
+// batch, i.e. two GEMMs per AMP iteration:  [LM x n] x [n x B]  and  [n x LM] x [LM x B].
+//
+// Precision scheme (FP32 emulation on the bf16 tensor pipe, "bf16x3"): every operand value x (fp64) is split into
+// three bf16 planes x0 = bf16(x), x1 = bf16(x - x0), x2 = bf16(x - x0 - x1)  (|x - x0 - x1 - x2| <= 2^-27 |x|).
+// A product a*b is evaluated as a0 b0 + (a0 b1 + a1 b0 + a0 b2 + a1 b1 + a2 b0): six tcgen05.mma passes whose
+// bf16 x bf16 products are exact in the fp32 accumulators; the three dropped terms are <= 2^-26 |a b|.  The
+// leading term and the five correction terms accumulate in two separate TMEM accumulators, so the corrections
+// are not rounded at the magnitude of the leading sum, and the K loop is cut into chunks: after every chunk the
+// epilogue warps drain both accumulators and add them in fp64 (hi + lo) to the output, which bounds the length
+// of any fp32 accumulation to one chunk (default 1024 values of k).
+//
+// Kernel: one CTA per (128-row tile of the A-side operand, BN codewords, K slice).  Warp 0 = TMA producer (3 + 3
+// bf16 planes per stage, 64-byte rows, SWIZZLE_64B), warp 1 = TMEM allocation + single-thread MMA issue
+// (12 tcgen05.mma per 32-k stage), warps 2-5 = epilogue (tcgen05.ld 32x32b, fp64 accumulate into the partial
+// output of the CTA's K slice).  Operands are K-major on both sides, so A is stored twice (A and A^T planes).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int GM = 128;      // UMMA M: rows of the A-side operand per CTA
+constexpr int GK = 32;       // k values per pipeline stage
+constexpr int GKB = GK * 2;  // bytes per smem row (bf16) = the swizzle span
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor of a K-major [rows][32 bf16] tile written by TMA with SWIZZLE_64B:
+// start address >> 4 in bits [0,14), leading byte offset field = 1 (unused by swizzled K-major layouts) in bits
+// [16,30), stride byte offset (8 rows * 64 B = 512 B) >> 4 in bits [32,46),
+// descriptor version 1 in bits [46,48), layout type SWIZZLE_64B = 4 in bits [61,64)
+// (cute/arch/mma_sm100_desc.hpp, union SmemDescriptor)
+__device__ __forceinline__ uint64_t kmajor_sw64_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+
+// instruction descriptor: D = fp32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc(int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int A_BYTES = 3 * GM * GKB, B_BYTES = 3 * BN * GKB, STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_BYTES = 8 * (2 * STAGES + 2) + 16;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + slack for the 1024-byte alignment
+};
+
+// out[slice][nn][mm] (=|+=) sum_k Aop[mm][k] * Bop[nn][k]   over the k-blocks of the CTA's slice
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   double *__restrict__ out, int M, int N, int ldo, long slice_stride, int nkb, int kb_per_slice,
+                   int kb_per_chunk) {
+    using S = GemmSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + STAGES * S::STAGE_BYTES;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
+    const uint32_t tfull = bars + 8u * (2 * STAGES), tempty = tfull + 8u, tslot = tempty + 8u;
+    uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t *tslot_ptr = reinterpret_cast<volatile uint32_t *>(gen_base + STAGES * S::STAGE_BYTES + 8 * (2 * STAGES + 2));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * GM, n0 = blockIdx.y * BN, slice = blockIdx.z;
+    const int kb0 = slice * kb_per_slice, kb1 = min(nkb, kb0 + kb_per_slice);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: [0, BN) leading-term accumulator, [BN, 2 BN) correction-term accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tslot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = kb0; kb < kb1; kb++) {
+                mbar_wait(empty(s), ph ^ 1u);
+                mbar_expect_tx(full(s), S::STAGE_BYTES);
+                const uint32_t dst = base + s * S::STAGE_BYTES;
+#pragma unroll
+                for (int p = 0; p < 3; p++) tma_load_3d(dst + p * GM * GKB, &tmA, full(s), kb * GK, m0, p);
+#pragma unroll
+                for (int p = 0; p < 3; p++) tma_load_3d(dst + S::A_BYTES + p * BN * GKB, &tmB, full(s), kb * GK, n0, p);
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issue (one thread)
+            constexpr uint32_t idesc = umma_idesc(BN);
+            const uint32_t d_hi = tmem, d_lo = tmem + BN;
+            int s = 0, chunk = 0;
+            uint32_t ph = 0, tph = 0;
+            for (int kb = kb0; kb < kb1;) {
+                if (chunk > 0) {  // the epilogue must have drained the previous chunk
+                    mbar_wait(tempty, tph);
+                    tph ^= 1u;
+                    tc_fence_after();
+                }
+                const int kend = min(kb1, kb + kb_per_chunk);
+                uint32_t acc = 0;
+                for (; kb < kend; kb++) {
+                    mbar_wait(full(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_base = base + s * S::STAGE_BYTES, b_base = a_base + S::A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < GK / 16; j++) {
+                        uint64_t ad[3], bd[3];
+#pragma unroll
+                        for (int p = 0; p < 3; p++) {
+                            ad[p] = kmajor_sw64_desc(a_base + p * GM * GKB + j * 32);
+                            bd[p] = kmajor_sw64_desc(b_base + p * BN * GKB + j * 32);
+                        }
+                        umma_bf16(d_hi, ad[0], bd[0], idesc, acc);
+                        umma_bf16(d_lo, ad[0], bd[1], idesc, acc);
+                        umma_bf16(d_lo, ad[1], bd[0], idesc, 1u);
+                        umma_bf16(d_lo, ad[0], bd[2], idesc, 1u);
+                        umma_bf16(d_lo, ad[1], bd[1], idesc, 1u);
+                        umma_bf16(d_lo, ad[2], bd[0], idesc, 1u);
+                        acc = 1u;
+                    }
+                    umma_commit(empty(s));  // frees the stage once these MMAs have read it
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(tfull);  // chunk complete -> epilogue
+                chunk++;
+            }
+        }
+    } else {  // ---- epilogue warps 2..5: TMEM lanes [32 g, 32 g + 32), g = warp % 4
+        const int g = warp & 3, row = g * 32 + lane, m = m0 + row;
+        const int nchunks = (kb1 - kb0 + kb_per_chunk - 1) / kb_per_chunk;
+        double *obase = out + (size_t)slice * slice_stride;
+        uint32_t fph = 0;
+        for (int c = 0; c < nchunks; c++) {
+            mbar_wait(tfull, fph);
+            fph ^= 1u;
+            tc_fence_after();
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 32; cb++) {
+                uint32_t hi[32], lo[32];
+                const uint32_t taddr = tmem + ((uint32_t)(g * 32) << 16) + cb * 32;
+                tmem_ld32(taddr, hi);
+                tmem_ld32(taddr + BN, lo);
+                tmem_ld_wait();
+                if (m < M) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        const int nn = n0 + cb * 32 + i;
+                        if (nn < N) {
+                            const double v = (double)__uint_as_float(hi[i]) + (double)__uint_as_float(lo[i]);
+                            double *p = obase + (size_t)nn * ldo + m;
+                            if (c == 0) *p = v; else *p += v;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * BN) : "memory");
+    }
+}
+
+// ---- operand preparation --------------------------------------------------------------------------------------
+__device__ __forceinline__ void split3(double x, __nv_bfloat16 &b0, __nv_bfloat16 &b1, __nv_bfloat16 &b2) {
+    b0 = __double2bfloat16(x);
+    const double r1 = x - (double)__bfloat162float(b0);
+    b1 = __double2bfloat16(r1);
+    const double r2 = r1 - (double)__bfloat162float(b1);
+    b2 = __double2bfloat16(r2);
+}
+
+// planes[p][r][k] (row stride Kp) = bf16x3 split of x[r][k] (row stride ldx)
+__global__ void split_rows_kernel(const double *__restrict__ x, long ldx, int rows, int K, int Kp,
+                                  __nv_bfloat16 *__restrict__ planes) {
+    const int r = blockIdx.y;
+    const size_t ps = (size_t)rows * Kp;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < Kp; k += gridDim.x * blockDim.x) {
+        __nv_bfloat16 b0, b1, b2;
+        split3(k < K ? x[(size_t)r * ldx + k] : 0.0, b0, b1, b2);
+        const size_t o = (size_t)r * Kp + k;
+        planes[o] = b0; planes[ps + o] = b1; planes[2 * ps + o] = b2;
+    }
+}
+
+// planes[p][c][r] (row stride Rp) = bf16x3 split of x[r][c]: the transposed operand (32 x 32 tiles through smem)
+__global__ void split_transpose_kernel(const double *__restrict__ x, int R, int C, int Rp,
+                                       __nv_bfloat16 *__restrict__ planes) {
+    __shared__ double tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < R && c < C) ? x[(size_t)r * C + c] : 0.0;
+    }
+    __syncthreads();
+    const size_t ps = (size_t)C * Rp;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < C && r < Rp) {
+            __nv_bfloat16 b0, b1, b2;
+            split3(tile[threadIdx.x][i], b0, b1, b2);
+            const size_t o = (size_t)c * Rp + r;
+            planes[o] = b0; planes[ps + o] = b1; planes[2 * ps + o] = b2;
+        }
+    }
+}
+
+// out[b][m] = (c_in ? c_in[b][m] : 0) + sign * sum_s part[s][b][m]
+__global__ void combine_kernel(const double *__restrict__ part, int slices, long slice_stride, const double *__restrict__ c_in,
+                               double sign, int ld, double *__restrict__ out) {
+    const int b = blockIdx.y;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < ld; m += gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int s = 0; s < slices; s++) acc += part[(size_t)s * slice_stride + (size_t)b * ld + m];
+        const size_t o = (size_t)b * ld + m;
+        out[o] = (c_in ? c_in[o] : 0.0) + sign * acc;
+    }
+}
+
+// ---- AMP iteration pieces (sparc_ldpc.py:203-220) -------------------------------------------------------------
+// s = beta + A^T z (partials summed in slice order); beta <- sqrt(n P_l) softmax_section(s sqrt(n P_l) / tau^2);
+// writes beta (fp64), its bf16x3 planes and sum(beta^2) per section.  One warp per section; inactive codewords
+// (early stop) are left untouched.
+__global__ void dense_denoise_kernel(const double *__restrict__ part, int slices, long slice_stride,
+                                     const double *__restrict__ Pl, const double *__restrict__ tau2,
+                                     const int *__restrict__ active, int L, int M, int n, int LMp, int B,
+                                     double *__restrict__ beta, __nv_bfloat16 *__restrict__ planes,
+                                     double *__restrict__ secsq) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int b = blockIdx.y, l = blockIdx.x * wpb + warp;
+    if (l >= L || !active[b]) return;
+    const size_t LM = (size_t)L * M;
+    const double rt = sqrt((double)n * Pl[l]), c2 = rt / tau2[b];
+    double *bsec = beta + (size_t)b * LM + (size_t)l * M;
+    const double *psec = part + (size_t)b * LM + (size_t)l * M;
+    double m = -INFINITY;
+    for (int j = lane; j < M; j += 32) {
+        double s = bsec[j];
+        for (int sl = 0; sl < slices; sl++) s += psec[(size_t)sl * slice_stride + j];
+        m = fmax(m, s * c2);
+    }
+    for (int d = 16; d; d >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, d));
+    double sum = 0.0;
+    for (int j = lane; j < M; j += 32) {
+        double s = bsec[j];
+        for (int sl = 0; sl < slices; sl++) s += psec[(size_t)sl * slice_stride + j];
+        sum += exp(s * c2 - m);
+    }
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const double sc = rt / sum;
+    double sq = 0.0;
+    const size_t ps = (size_t)B * LMp;
+    __nv_bfloat16 *pl = planes + (size_t)b * LMp + (size_t)l * M;
+    for (int j = lane; j < M; j += 32) {
+        double s = bsec[j];
+        for (int sl = 0; sl < slices; sl++) s += psec[(size_t)sl * slice_stride + j];
+        const double v = exp(s * c2 - m) * sc;
+        bsec[j] = v;
+        sq += v * v;
+        __nv_bfloat16 b0, b1, b2;
+        split3(v, b0, b1, b2);
+        pl[j] = b0; pl[ps + j] = b1; pl[2 * ps + j] = b2;
+    }
+    for (int d = 16; d; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+    if (lane == 0) secsq[(size_t)b * L + l] = sq;
+}
+
+// One CTA per codeword.  mode 0 (start): z = y - (part ? sum_s part : 0).  mode 1 (iteration t):
+// z <- y - A beta + (z / tau^2) (P - |beta|^2 / n)   (:220).  Then tau' = sqrt(|z|^2 / n) (:203) and the stop rule
+// (:204): tau' == tau, or |tau' - tau| <= 2^-27 tau because operands rounded to 2^-27 cannot reach an exact fp64
+// fixed point.  Writes z (fp64), its bf16x3 planes, tau^2 for the next iteration, and the per-codeword state.
+__global__ void dense_residual_kernel(int mode, int t, const double *__restrict__ part, int slices, long slice_stride,
+                                      const double *__restrict__ y, const double *__restrict__ secsq,
+                                      const double *__restrict__ Pl, int L, int n, int np, int B, double *__restrict__ z,
+                                      __nv_bfloat16 *__restrict__ planes, double *__restrict__ tau2, double *__restrict__ last_tau,
+                                      int *__restrict__ active, int *__restrict__ iters, int *__restrict__ n_exec,
+                                      unsigned *__restrict__ flags, double *__restrict__ tau2_trace, int T,
+                                      int *__restrict__ n_active) {
+    __shared__ double red[40];
+    const int b = blockIdx.x;
+    if (mode == 1 && !active[b]) return;
+    double coef = 0.0;
+    if (mode == 1) {
+        double sq = 0.0, pw = 0.0;
+        for (int l = threadIdx.x; l < L; l += blockDim.x) { sq += secsq[(size_t)b * L + l]; pw += Pl[l]; }
+        const double sumsq = block_sum(sq, red), P = block_sum(pw, red);
+        coef = (P - sumsq / (double)n) / tau2[b];
+    }
+    const size_t ps = (size_t)B * np;
+    double acc2 = 0.0;
+    for (int k = threadIdx.x; k < np; k += blockDim.x) {
+        double v = 0.0;
+        if (k < n) {
+            double x = 0.0;
+            if (part) for (int s = 0; s < slices; s++) x += part[(size_t)s * slice_stride + (size_t)b * n + k];
+            v = y[(size_t)b * n + k] - x;
+            if (mode == 1) v += z[(size_t)b * n + k] * coef;
+            z[(size_t)b * n + k] = v;
+            acc2 += v * v;
+        }
+        __nv_bfloat16 b0, b1, b2;
+        split3(v, b0, b1, b2);
+        const size_t o = (size_t)b * np + k;
+        planes[o] = b0; planes[ps + o] = b1; planes[2 * ps + o] = b2;
+    }
+    const double tau = sqrt(block_sum(acc2, red) / (double)n);
+    if (threadIdx.x == 0) {
+        const int tn = (mode == 0) ? 0 : t + 1;  // index of the iteration that would use this tau
+        if (mode == 1) n_exec[b] += 1;
+        const double lt = last_tau[b];
+        if (mode == 1 && tn < T && (tau == lt || fabs(tau - lt) <= lt * 7.450580596923828e-09)) {
+            active[b] = 0;
+            iters[b] = tn;
+            flags[b] |= SB_AMP_STOPPED;
+            atomicSub(n_active, 1);
+        } else {
+            last_tau[b] = tau;
+            tau2[b] = tau * tau;
+            if (tau2_trace && tn < T) tau2_trace[(size_t)b * T + tn] = tau * tau;
+        }
+    }
+}
+
+__global__ void dense_init_state_kernel(int B, int T, int *active, int *iters, int *n_exec, unsigned *flags, double *last_tau,
+                                        int *n_active) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) *n_active = B;
+    if (b >= B) return;
+    active[b] = 1;
+    iters[b] = T > 0 ? T - 1 : 0;
+    n_exec[b] = 0;
+    flags[b] = 0;
+    last_tau[b] = 0.0;
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled g_encode = nullptr;
+
+static int get_encode() {
+    if (g_encode) return SB_OK;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return fail(SB_ECUDA, "cuTensorMapEncodeTiled is not available from the driver%s", "");
+    g_encode = (PFN_cuTensorMapEncodeTiled)fn;
+    return SB_OK;
+}
+
+// tensor map over bf16 planes [3][rows][Kp] with logical extents (K, rows, 3): boxes of (32 k, box_rows, 1 plane),
+// 64-byte swizzle, out-of-range elements read as zero
+static int make_map(CUtensorMap *tm, const void *planes, int rows, int K, int Kp, int box_rows) {
+    if (get_encode() != SB_OK) return SB_ECUDA;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 3};
+    cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)rows * Kp * 2};
+    cuuint32_t box[3] = {GK, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(planes), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SB_ECUDA, "cuTensorMapEncodeTiled failed%s (%ld)", "", (long)r);
+    return SB_OK;
+}
+
+static int pad8(int v) { return (v + 7) & ~7; }
+
+}  // namespace sb
+
+using namespace sb;
+
+struct sb_dense {
+    int n, LM, np, LMp;       // np / LMp = row strides of the planes (multiples of 8 values = 16 bytes)
+    __nv_bfloat16 *A;         // [3][n][LMp]   rows of A       (A-side operand of A beta:  M = n,  K = LM)
+    __nv_bfloat16 *At;        // [3][LM][np]   rows of A^T     (A-side operand of A^T z:   M = LM, K = n)
+    CUtensorMap mapA, mapAt;
+    int sms;
+    // workspace, grown on demand
+    int capB;
+    __nv_bfloat16 *zpl, *bpl;  // [3][capB][np], [3][capB][LMp]
+    double *part;              // max(slices_z * capB * LM, slices_b * capB * n)
+    size_t part_elems;
+    double *z, *tau2, *last_tau, *secsq;
+    int *active, *n_active;
+    int secsq_L;
+};
+
+static void dense_free_ws(sb_dense *d) {
+    cudaFree(d->zpl); cudaFree(d->bpl); cudaFree(d->part); cudaFree(d->z); cudaFree(d->tau2); cudaFree(d->last_tau);
+    cudaFree(d->secsq); cudaFree(d->active); cudaFree(d->n_active);
+    d->zpl = d->bpl = nullptr; d->part = d->z = d->tau2 = d->last_tau = d->secsq = nullptr; d->active = d->n_active = nullptr;
+    d->capB = 0; d->part_elems = 0; d->secsq_L = 0;
+}
+
+// K slices: enough CTAs to fill the GPU (the A beta product has only n / 128 row tiles), never more than k-blocks
+static void plan_slices(const sb_dense *d, int Mrows, int K, int B, int BN, int *slices, int *kb_per_slice) {
+    const int nkb = (K + GK - 1) / GK;
+    const int tiles = ((Mrows + GM - 1) / GM) * ((B + BN - 1) / BN);
+    int s = (2 * d->sms + tiles - 1) / tiles;
+    if (s < 1) s = 1;
+    if (s > 64) s = 64;
+    if (s > nkb) s = nkb;
+    int per = (nkb + s - 1) / s;
+    const char *env = getenv("SB_DENSE_CHUNK_KB");
+    const int chunk = env ? atoi(env) : 32;
+    if (per > chunk) per = ((per + chunk - 1) / chunk) * chunk;  // whole chunks per slice
+    *kb_per_slice = per;
+    *slices = (nkb + per - 1) / per;
+}
+
+static int pick_bn(int B) {
+    const char *env = getenv("SB_DENSE_BN");
+    if (env) return atoi(env) == 256 ? 256 : 128;
+    return B > 128 ? 256 : 128;
+}
+
+static int dense_reserve(sb_dense *d, int B, int L) {
+    size_t need_part = 0;
+    {
+        int s1, p1, s2, p2;
+        const int BN = pick_bn(B);
+        plan_slices(d, d->LM, d->n, B, BN, &s1, &p1);
+        plan_slices(d, d->n, d->LM, B, BN, &s2, &p2);
+        need_part = std::max((size_t)s1 * B * d->LM, (size_t)s2 * B * d->n);
+    }
+    if (B <= d->capB && need_part <= d->part_elems && L <= d->secsq_L) return SB_OK;
+    dense_free_ws(d);
+    SB_CUDA(cudaMalloc(&d->zpl, sizeof(__nv_bfloat16) * 3 * (size_t)B * d->np));
+    SB_CUDA(cudaMalloc(&d->bpl, sizeof(__nv_bfloat16) * 3 * (size_t)B * d->LMp));
+    SB_CUDA(cudaMalloc(&d->part, sizeof(double) * need_part));
+    SB_CUDA(cudaMalloc(&d->z, sizeof(double) * (size_t)B * d->n));
+    SB_CUDA(cudaMalloc(&d->tau2, sizeof(double) * B));
+    SB_CUDA(cudaMalloc(&d->last_tau, sizeof(double) * B));
+    SB_CUDA(cudaMalloc(&d->secsq, sizeof(double) * (size_t)B * (L > 0 ? L : 1)));
+    SB_CUDA(cudaMalloc(&d->active, sizeof(int) * B));
+    SB_CUDA(cudaMalloc(&d->n_active, sizeof(int)));
+    d->capB = B; d->part_elems = need_part; d->secsq_L = L > 0 ? L : 1;
+    return SB_OK;
+}
+
+// part[s][b][m] = sum over slice s of Aop[m][k] * xplanes[b][k];  transpose = 0: Aop = A (M = n, K = LM), 1: A^T
+static int dense_gemm_launch(const sb_dense *d, int transpose, const __nv_bfloat16 *xpl, int B, double *part,
+                             int *slices_out, long *slice_stride_out, cudaStream_t st) {
+    const int Mrows = transpose ? d->LM : d->n, K = transpose ? d->n : d->LM, Kp = transpose ? d->np : d->LMp;
+    const int BN = pick_bn(B);
+    CUtensorMap mapB;
+    int rc = make_map(&mapB, xpl, B, K, Kp, BN);
+    if (rc != SB_OK) return rc;
+    int slices, per;
+    plan_slices(d, Mrows, K, B, BN, &slices, &per);
+    const int nkb = (K + GK - 1) / GK;
+    const char *env = getenv("SB_DENSE_CHUNK_KB");
+    const int chunk = env ? atoi(env) : 32;
+    const long sstride = (long)B * Mrows;
+    dim3 grid((Mrows + GM - 1) / GM, (B + BN - 1) / BN, slices);
+    const CUtensorMap &mapA = transpose ? d->mapAt : d->mapA;
+    if (BN == 256) {
+        using S = GemmSmem<256, 3>;
+        SB_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        gemm_bf16x3_kernel<256, 3><<<grid, 192, S::TOTAL, st>>>(mapA, mapB, part, Mrows, B, Mrows, sstride, nkb, per, chunk);
+    } else {
+        using S = GemmSmem<128, 4>;
+        SB_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        gemm_bf16x3_kernel<128, 4><<<grid, 192, S::TOTAL, st>>>(mapA, mapB, part, Mrows, B, Mrows, sstride, nkb, per, chunk);
+    }
+    SB_LAUNCHED();
+    *slices_out = slices;
+    *slice_stride_out = sstride;
+    return SB_OK;
+}
+
+extern "C" int sb_dense_create(const double *A_dev, int n, int LM, sb_dense **out) {
+    if (!A_dev || !out || n <= 0 || LM <= 0) return fail(SB_EINVAL, "sb_dense_create: bad argument%s", "");
+    int dev = 0, major = 0, sms = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    SB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    SB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (major != 10) return fail(SB_ECUDA, "sb_dense_create: the tcgen05 GEMM needs an sm_100 device%s (found major %ld)", "", major);
+    sb_dense *d = new sb_dense();
+    memset(d, 0, sizeof(*d));
+    d->n = n; d->LM = LM; d->np = pad8(n); d->LMp = pad8(LM); d->sms = sms;
+    cudaError_t e1 = cudaMalloc(&d->A, sizeof(__nv_bfloat16) * 3 * (size_t)n * d->LMp);
+    cudaError_t e2 = cudaMalloc(&d->At, sizeof(__nv_bfloat16) * 3 * (size_t)LM * d->np);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        cudaFree(d->A); cudaFree(d->At); delete d;
+        return fail(SB_ENOMEM, "sb_dense_create: cudaMalloc failed%s", "");
+    }
+    {
+        dim3 g((d->LMp + 255) / 256 < 1024 ? (d->LMp + 255) / 256 : 1024, n);
+        split_rows_kernel<<<g, 256>>>(A_dev, LM, n, LM, d->LMp, d->A);
+        g_launches.fetch_add(1);
+        dim3 gt((LM + 31) / 32, (d->np + 31) / 32);
+        split_transpose_kernel<<<gt, dim3(32, 8)>>>(A_dev, n, LM, d->np, d->At);
+        g_launches.fetch_add(1);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(d->A); cudaFree(d->At); delete d; return fail(SB_ECUDA, "sb_dense_create: %s", cudaGetErrorString(e)); }
+    int rc = make_map(&d->mapA, d->A, n, LM, d->LMp, GM);
+    if (rc == SB_OK) rc = make_map(&d->mapAt, d->At, LM, n, d->np, GM);
+    if (rc != SB_OK) { cudaFree(d->A); cudaFree(d->At); delete d; return rc; }
+    *out = d;
+    return SB_OK;
+}
+
+extern "C" void sb_dense_destroy(sb_dense *d) {
+    if (!d) return;
+    dense_free_ws(d);
+    cudaFree(d->A);
+    cudaFree(d->At);
+    delete d;
+}
+
+// out[b] = A x[b] (transpose = 0: x [B][LM] -> out [B][n]) or A^T x[b] (transpose = 1: x [B][n] -> out [B][LM])
+extern "C" int sb_dense_apply_batch(sb_dense *d, int transpose, const double *x, int B, double *out, void *stream) {
+    if (!d || !x || !out || B < 0) return fail(SB_EINVAL, "sb_dense_apply_batch: bad argument%s", "");
+    if (B == 0) return SB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = dense_reserve(d, B, 1);
+    if (rc != SB_OK) return rc;
+    const int K = transpose ? d->n : d->LM, Kp = transpose ? d->np : d->LMp, Mrows = transpose ? d->LM : d->n;
+    __nv_bfloat16 *pl = transpose ? d->zpl : d->bpl;
+    dim3 g((Kp + 255) / 256 < 1024 ? (Kp + 255) / 256 : 1024, B);
+    split_rows_kernel<<<g, 256, 0, st>>>(x, K, B, K, Kp, pl);
+    SB_LAUNCHED();
+    int slices; long ss;
+    rc = dense_gemm_launch(d, transpose, pl, B, d->part, &slices, &ss, st);
+    if (rc != SB_OK) return rc;
+    dim3 gc((Mrows + 255) / 256 < 1024 ? (Mrows + 255) / 256 : 1024, B);
+    combine_kernel<<<gc, 256, 0, st>>>(d->part, slices, ss, nullptr, 1.0, Mrows, out);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+// Batched AMP decode with the dense operator (sparc_ldpc.py:189-222).  All pointers are device pointers:
+// y [B][n], Pl [L], beta0 [B][L*M] or NULL, beta [B][L*M] out, iters / n_exec / flags [B] out,
+// tau2_trace [B][T] or NULL.  The loop stops early once every codeword has stopped (checked every 4 iterations).
+extern "C" int sb_dense_amp_batch(sb_dense *d, const double *y, const double *Pl, const double *beta0, int L, int M, int B,
+                                  int T, double *beta, int *iters, int *n_exec, unsigned *flags, double *tau2_trace,
+                                  void *stream) {
+    if (!d || !y || !Pl || !beta || !iters || !n_exec || !flags || B < 0 || T < 0 || L <= 0 || M <= 0)
+        return fail(SB_EINVAL, "sb_dense_amp_batch: bad argument%s", "");
+    if ((long)L * M != d->LM) return fail(SB_EINVAL, "sb_dense_amp_batch: L*M does not match the matrix%s (%ld)", "", (long)L * M);
+    if (B == 0) return SB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = dense_reserve(d, B, L);
+    if (rc != SB_OK) return rc;
+    const int n = d->n, LM = d->LM;
+    dense_init_state_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, T, d->active, iters, n_exec, flags, d->last_tau, d->n_active);
+    SB_LAUNCHED();
+    if (tau2_trace) SB_CUDA(cudaMemsetAsync(tau2_trace, 0xFF, sizeof(double) * (size_t)B * T, st));  // NaN = not executed
+    int slices = 0; long ss = 0;
+    if (beta0) {  // z = y - A beta0   (:197-198)
+        if (beta0 != beta) SB_CUDA(cudaMemcpyAsync(beta, beta0, sizeof(double) * (size_t)B * LM, cudaMemcpyDeviceToDevice, st));
+        dim3 g((d->LMp + 255) / 256 < 1024 ? (d->LMp + 255) / 256 : 1024, B);
+        split_rows_kernel<<<g, 256, 0, st>>>(beta, LM, B, LM, d->LMp, d->bpl);
+        SB_LAUNCHED();
+        rc = dense_gemm_launch(d, 0, d->bpl, B, d->part, &slices, &ss, st);
+        if (rc != SB_OK) return rc;
+    } else {
+        SB_CUDA(cudaMemsetAsync(beta, 0, sizeof(double) * (size_t)B * LM, st));
+    }
+    dense_residual_kernel<<<B, 256, 0, st>>>(0, 0, beta0 ? d->part : nullptr, slices, ss, y, d->secsq, Pl, L, n, d->np, B, d->z,
+                                             d->zpl, d->tau2, d->last_tau, d->active, iters, n_exec, flags, tau2_trace, T,
+                                             d->n_active);
+    SB_LAUNCHED();
+    for (int t = 0; t < T; t++) {
+        rc = dense_gemm_launch(d, 1, d->zpl, B, d->part, &slices, &ss, st);  // A^T z
+        if (rc != SB_OK) return rc;
+        dim3 gd((L + 7) / 8, B);
+        dense_denoise_kernel<<<gd, 256, 0, st>>>(d->part, slices, ss, Pl, d->tau2, d->active, L, M, n, d->LMp, B, beta, d->bpl,
+                                                 d->secsq);
+        SB_LAUNCHED();
+        rc = dense_gemm_launch(d, 0, d->bpl, B, d->part, &slices, &ss, st);  // A beta
+        if (rc != SB_OK) return rc;
+        dense_residual_kernel<<<B, 256, 0, st>>>(1, t, d->part, slices, ss, y, d->secsq, Pl, L, n, d->np, B, d->z, d->zpl,
+                                                 d->tau2, d->last_tau, d->active, iters, n_exec, flags, tau2_trace, T,
+                                                 d->n_active);
+        SB_LAUNCHED();
+        if ((t & 3) == 3 && t + 1 < T) {
+            int na = 0;
+            SB_CUDA(cudaMemcpyAsync(&na, d->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            SB_CUDA(cudaStreamSynchronize(st));
+            if (na <= 0) break;
+        }
+    }
+    return SB_OK;
+}

@@ -225,12 +225,48 @@ def test_gaussian_design_matrix_c1(S, oracle):
                             lambda v: (A.T @ np.asarray(v).reshape(-1)).reshape(-1, 1), trace=tr)
         err = relinf(beta[b], ref.reshape(-1))
         print("Gaussian C1 codeword %d: rel err beta %.2e, iterations %d (ref %d)" % (b, err, iters[b], t))
-        assert err < TIGHT and (abs(int(iters[b]) - t) <= 6 or int(iters[b]) == T - 1 or t == T - 1)
+        # tcgen05 GEMMs with bf16x3 operands (FP32 emulation): north-star tolerance 1e-5, measured ~1e-7
+        assert err < NORTH_STAR_RTOL and int(iters[b]) <= t
         assert np.array_equal(beta[b].reshape(L, M).argmax(1), ref.reshape(L, M).argmax(1))
+    # per-iteration tau^2 of the batch against the oracle's trace
+    res = Ab._sb_op.amp(torch.from_numpy(np.array(ys)).cuda(), torch.from_numpy(Pl).cuda(), T, trace=True)
+    tau2 = res.tau2.cpu().numpy()
+    for b in range(3):
+        tr = []
+        oracle.amp(ys[b].reshape(-1, 1), Pl, L, M, T, lambda v: (A @ np.asarray(v).reshape(-1)).reshape(-1, 1),
+                   lambda v: (A.T @ np.asarray(v).reshape(-1)).reshape(-1, 1), trace=tr)
+        k = int(res.n_exec[b])
+        want = np.array([x[0] for x in tr[:k]])
+        got = tau2[b, :k]
+        err = np.max(np.abs(got - want) / want)
+        print("Gaussian C1 codeword %d: %d iterations, max rel err tau^2 %.2e" % (b, k, err))
+        assert err < NORTH_STAR_RTOL
     # the single-codeword reference signature takes the dense closures too
     b1 = S.amp(ys[0].reshape(-1, 1), None, Pl, L, M, T, Ab, Az).reshape(-1)
     assert relinf(b1, beta[0]) < 1e-12
-    assert Ab(beta[0]).shape == (n, 1) and relinf(Ab(beta[0]).reshape(-1), A @ beta[0]) < 1e-12
+    assert Ab(beta[0]).shape == (n, 1) and relinf(Ab(beta[0]).reshape(-1), A @ beta[0]) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(256, 512, 100), (130, 200, 7), (384, 1000, 129), (4608, 2048, 40), (640, 40000, 130)])
+def test_dense_gemm_bf16x3_against_fp64(Eng, shape):
+    """The tcgen05 / TMA GEMM of the Gaussian mode alone: A x and A^T x for ragged shapes (rows not a multiple of
+    128, k not a multiple of 32, batches on both sides of the 128 / 256 tile widths, several K slices) against
+    numpy fp64.  Error model: operands carried to 2^-27, products to 2^-26, fp32 accumulation over chunks of 1024 k -> a few 1e-7 of |A| |x|."""
+    n, LM, B = shape
+    rs = np.random.RandomState(n + LM + B)
+    A = rs.randn(n, LM) / np.sqrt(n)
+    op = Eng.DenseOperator(A, 1, LM)
+    x = rs.randn(B, LM) * np.exp(rs.randn(B, LM))
+    z = rs.randn(B, n)
+    got = op.Ab(torch.from_numpy(x).cuda()).cpu().numpy()
+    want = x @ A.T
+    scale = np.abs(x) @ np.abs(A.T)
+    e1 = np.max(np.abs(got - want) / scale)
+    got2 = op.Az(torch.from_numpy(z).cuda()).cpu().numpy()
+    want2 = z @ A
+    e2 = np.max(np.abs(got2 - want2) / (np.abs(z) @ np.abs(A)))
+    print("dense GEMM n=%d LM=%d B=%d: max err / (|A||x|): A x %.2e, A^T z %.2e" % (n, LM, B, e1, e2))
+    assert e1 < 5e-7 and e2 < 5e-7
 
 
 @pytest.mark.parametrize("mode", ["strict", "fast"])
