@@ -216,13 +216,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 tmem_ld32(taddr + BN, lo);
                 tmem_ld_wait();
                 if (m < M) {
+                    // the CTA owns this slice of the output: the first chunk stores, later chunks add with a
+                    // fire-and-forget reduction (RED.ADD.F64), so no load round trip sits between TMEM reads
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
                         const int nn = n0 + cb * 32 + i;
                         if (nn < N) {
                             const double v = (double)__uint_as_float(hi[i]) + (double)__uint_as_float(lo[i]);
                             double *p = obase + (size_t)nn * ldo + m;
-                            if (c == 0) *p = v; else *p += v;
+                            if (c == 0) *p = v; else atomicAdd(p, v);
                         }
                     }
                 }
