@@ -169,6 +169,18 @@ int sb_dense_apply_batch(sb_dense *d, int transpose, const double *x, int B, dou
 int sb_dense_amp_batch(sb_dense *d, const double *y, const double *Pl, const double *beta0, int L, int M, int B, int T,
                        double *beta, int *iters, int *n_exec, unsigned *flags, double *tau2_trace, void *stream);
 
+/* Column-sharded dense matrix (for an A that exceeds one GPU's HBM): the handle holds the columns of L_local
+ * sections; Pl_local / beta0_local / beta_local refer to them, P_total = sum of Pl over ALL sections; y, z and
+ * tau^2 are replicated on every rank.  A^T z, the softmax and |beta|^2 are local; once per iteration the library
+ * calls `allreduce(ctx, xbuf, B*n + B, stream)`, which must sum xbuf (partial A beta [B][n] followed by |beta|^2
+ * [B], device memory owned by the caller) over all ranks in place, ordered on `stream`, and return 0.  With
+ * NCCL: ncclAllReduce(xbuf, xbuf, count, ncclDouble, ncclSum, comm, stream). */
+typedef int (*sb_allreduce_fn)(void *ctx, double *buf_dev, long count, void *stream);
+int sb_dense_amp_batch_sharded(sb_dense *d, const double *y, const double *Pl_local, double P_total,
+                               const double *beta0_local, int L_local, int M, int B, int T, double *beta_local, int *iters,
+                               int *n_exec, unsigned *flags, double *tau2_trace, double *xbuf, sb_allreduce_fn allreduce,
+                               void *ctx, void *stream);
+
 /* idx[b][i] = argmax of section i of beta[b] (first maximum wins, sparc_ldpc.py:640-643) */
 int sb_argmax_batch(const double *beta, long beta_stride, int count, int M, int B, int *idx, long idx_stride,
                     void *stream);

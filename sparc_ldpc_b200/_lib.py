@@ -48,6 +48,7 @@ SIGNATURES = {
     "sb_dense_destroy": (None, [_vp]),
     "sb_dense_apply_batch": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "sb_dense_amp_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_dense_amp_batch_sharded": (_i, [_vp, _vp, _vp, _d, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_argmax_batch": (_i, [_vp, _l, _i, _i, _i, _vp, _l, _vp]),
     "sb_llr2idx_batch": (_i, [_vp, _l, _i, _i, _i, _vp, _l, _vp]),
     "sb_count_errors_batch": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

@@ -298,6 +298,16 @@ __global__ void combine_kernel(const double *__restrict__ part, int slices, long
     }
 }
 
+// out[b] = sum_l secsq[b][l] (deterministic block sum); zero for inactive codewords
+__global__ void dense_sumsq_kernel(const double *__restrict__ secsq, int L, const int *__restrict__ active, double *__restrict__ out) {
+    __shared__ double red[40];
+    const int b = blockIdx.x;
+    double sq = 0.0;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) sq += secsq[(size_t)b * L + l];
+    const double v = block_sum(sq, red);
+    if (threadIdx.x == 0) out[b] = v;
+}
+
 // ---- AMP iteration pieces (sparc_ldpc.py:203-220) -------------------------------------------------------------
 // s = beta + A^T z (partials summed in slice order); beta <- sqrt(n P_l) softmax_section(s sqrt(n P_l) / tau^2);
 // writes beta (fp64), its bf16x3 planes and sum(beta^2) per section.  One warp per section; inactive codewords
@@ -356,15 +366,22 @@ __global__ void dense_residual_kernel(int mode, int t, const double *__restrict_
                                       __nv_bfloat16 *__restrict__ planes, double *__restrict__ tau2, double *__restrict__ last_tau,
                                       int *__restrict__ active, int *__restrict__ iters, int *__restrict__ n_exec,
                                       unsigned *__restrict__ flags, double *__restrict__ tau2_trace, int T,
-                                      int *__restrict__ n_active) {
+                                      int *__restrict__ n_active, const double *__restrict__ sumsq_ext, double P_ext) {
     __shared__ double red[40];
     const int b = blockIdx.x;
     if (mode == 1 && !active[b]) return;
     double coef = 0.0;
     if (mode == 1) {
-        double sq = 0.0, pw = 0.0;
-        for (int l = threadIdx.x; l < L; l += blockDim.x) { sq += secsq[(size_t)b * L + l]; pw += Pl[l]; }
-        const double sumsq = block_sum(sq, red), P = block_sum(pw, red);
+        double sumsq, P;
+        if (sumsq_ext) {  // column-sharded A: |beta|^2 and P summed over all ranks
+            sumsq = sumsq_ext[b];
+            P = P_ext;
+        } else {
+            double sq = 0.0, pw = 0.0;
+            for (int l = threadIdx.x; l < L; l += blockDim.x) { sq += secsq[(size_t)b * L + l]; pw += Pl[l]; }
+            sumsq = block_sum(sq, red);
+            P = block_sum(pw, red);
+        }
         coef = (P - sumsq / (double)n) / tau2[b];
     }
     const size_t ps = (size_t)B * np;
@@ -614,14 +631,14 @@ extern "C" int sb_dense_apply_batch(sb_dense *d, int transpose, const double *x,
 // Batched AMP decode with the dense operator (sparc_ldpc.py:189-222).  All pointers are device pointers:
 // y [B][n], Pl [L], beta0 [B][L*M] or NULL, beta [B][L*M] out, iters / n_exec / flags [B] out,
 // tau2_trace [B][T] or NULL.  The loop stops early once every codeword has stopped (checked every 4 iterations).
-extern "C" int sb_dense_amp_batch(sb_dense *d, const double *y, const double *Pl, const double *beta0, int L, int M, int B,
-                                  int T, double *beta, int *iters, int *n_exec, unsigned *flags, double *tau2_trace,
-                                  void *stream) {
-    if (!d || !y || !Pl || !beta || !iters || !n_exec || !flags || B < 0 || T < 0 || L <= 0 || M <= 0)
-        return fail(SB_EINVAL, "sb_dense_amp_batch: bad argument%s", "");
-    if ((long)L * M != d->LM) return fail(SB_EINVAL, "sb_dense_amp_batch: L*M does not match the matrix%s (%ld)", "", (long)L * M);
-    if (B == 0) return SB_OK;
-    cudaStream_t st = (cudaStream_t)stream;
+//
+// Column-sharded mode (allreduce != NULL): this handle holds the columns of L local sections of a larger matrix;
+// Pl / beta0 / beta refer to the local sections, P_total = sum of Pl over ALL sections, z and tau^2 are replicated
+// on every rank.  A^T z, the softmax and |beta|^2 are local; the partial A beta of every rank plus its |beta|^2
+// ([B][n] + [B] doubles in xbuf) are summed over the ranks by the caller's `allreduce` once per iteration.
+static int dense_amp_impl(sb_dense *d, const double *y, const double *Pl, double P_total, const double *beta0, int L, int M,
+                          int B, int T, double *beta, int *iters, int *n_exec, unsigned *flags, double *tau2_trace,
+                          sb_allreduce_fn allreduce, void *ctx, double *xbuf, cudaStream_t st) {
     int rc = dense_reserve(d, B, L);
     if (rc != SB_OK) return rc;
     const int n = d->n, LM = d->LM;
@@ -629,6 +646,24 @@ extern "C" int sb_dense_amp_batch(sb_dense *d, const double *y, const double *Pl
     SB_LAUNCHED();
     if (tau2_trace) SB_CUDA(cudaMemsetAsync(tau2_trace, 0xFF, sizeof(double) * (size_t)B * T, st));  // NaN = not executed
     int slices = 0; long ss = 0;
+    // after a GEMM of partial A beta: (sharded) fold the K slices into xbuf, append |beta|^2, sum over the ranks
+    auto exchange = [&](bool with_sumsq) -> int {
+        if (!allreduce) return SB_OK;
+        dim3 gc((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024, B);
+        combine_kernel<<<gc, 256, 0, st>>>(d->part, slices, ss, nullptr, 1.0, n, xbuf);
+        SB_LAUNCHED();
+        if (with_sumsq) {
+            dense_sumsq_kernel<<<B, 128, 0, st>>>(d->secsq, L, d->active, xbuf + (size_t)B * n);
+            SB_LAUNCHED();
+        } else {
+            SB_CUDA(cudaMemsetAsync(xbuf + (size_t)B * n, 0, sizeof(double) * B, st));
+        }
+        const int r = allreduce(ctx, xbuf, (long)B * n + B, (void *)st);
+        if (r != 0) return fail(SB_ECUDA, "sb_dense_amp_batch_sharded: the allreduce callback failed%s (%ld)", "", (long)r);
+        return SB_OK;
+    };
+    const double *xsrc = allreduce ? xbuf : d->part;
+    const double *sq_ext = allreduce ? xbuf + (size_t)B * n : nullptr;
     if (beta0) {  // z = y - A beta0   (:197-198)
         if (beta0 != beta) SB_CUDA(cudaMemcpyAsync(beta, beta0, sizeof(double) * (size_t)B * LM, cudaMemcpyDeviceToDevice, st));
         dim3 g((d->LMp + 255) / 256 < 1024 ? (d->LMp + 255) / 256 : 1024, B);
@@ -636,12 +671,14 @@ extern "C" int sb_dense_amp_batch(sb_dense *d, const double *y, const double *Pl
         SB_LAUNCHED();
         rc = dense_gemm_launch(d, 0, d->bpl, B, d->part, &slices, &ss, st);
         if (rc != SB_OK) return rc;
+        rc = exchange(false);
+        if (rc != SB_OK) return rc;
     } else {
         SB_CUDA(cudaMemsetAsync(beta, 0, sizeof(double) * (size_t)B * LM, st));
     }
-    dense_residual_kernel<<<B, 256, 0, st>>>(0, 0, beta0 ? d->part : nullptr, slices, ss, y, d->secsq, Pl, L, n, d->np, B, d->z,
-                                             d->zpl, d->tau2, d->last_tau, d->active, iters, n_exec, flags, tau2_trace, T,
-                                             d->n_active);
+    dense_residual_kernel<<<B, 256, 0, st>>>(0, 0, beta0 ? xsrc : nullptr, allreduce ? 1 : slices, allreduce ? (long)B * n : ss, y,
+                                             d->secsq, Pl, L, n, d->np, B, d->z, d->zpl, d->tau2, d->last_tau, d->active, iters,
+                                             n_exec, flags, tau2_trace, T, d->n_active, sq_ext, P_total);
     SB_LAUNCHED();
     for (int t = 0; t < T; t++) {
         rc = dense_gemm_launch(d, 1, d->zpl, B, d->part, &slices, &ss, st);  // A^T z
@@ -652,11 +689,13 @@ extern "C" int sb_dense_amp_batch(sb_dense *d, const double *y, const double *Pl
         SB_LAUNCHED();
         rc = dense_gemm_launch(d, 0, d->bpl, B, d->part, &slices, &ss, st);  // A beta
         if (rc != SB_OK) return rc;
-        dense_residual_kernel<<<B, 256, 0, st>>>(1, t, d->part, slices, ss, y, d->secsq, Pl, L, n, d->np, B, d->z, d->zpl,
-                                                 d->tau2, d->last_tau, d->active, iters, n_exec, flags, tau2_trace, T,
-                                                 d->n_active);
+        rc = exchange(true);
+        if (rc != SB_OK) return rc;
+        dense_residual_kernel<<<B, 256, 0, st>>>(1, t, xsrc, allreduce ? 1 : slices, allreduce ? (long)B * n : ss, y, d->secsq, Pl,
+                                                 L, n, d->np, B, d->z, d->zpl, d->tau2, d->last_tau, d->active, iters, n_exec,
+                                                 flags, tau2_trace, T, d->n_active, sq_ext, P_total);
         SB_LAUNCHED();
-        if ((t & 3) == 3 && t + 1 < T) {
+        if ((t & 3) == 3 && t + 1 < T) {  // z and tau are replicated bit for bit, so every rank takes the same exit
             int na = 0;
             SB_CUDA(cudaMemcpyAsync(&na, d->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
             SB_CUDA(cudaStreamSynchronize(st));
@@ -664,4 +703,29 @@ extern "C" int sb_dense_amp_batch(sb_dense *d, const double *y, const double *Pl
         }
     }
     return SB_OK;
+}
+
+extern "C" int sb_dense_amp_batch(sb_dense *d, const double *y, const double *Pl, const double *beta0, int L, int M, int B,
+                                  int T, double *beta, int *iters, int *n_exec, unsigned *flags, double *tau2_trace,
+                                  void *stream) {
+    if (!d || !y || !Pl || !beta || !iters || !n_exec || !flags || B < 0 || T < 0 || L <= 0 || M <= 0)
+        return fail(SB_EINVAL, "sb_dense_amp_batch: bad argument%s", "");
+    if ((long)L * M != d->LM) return fail(SB_EINVAL, "sb_dense_amp_batch: L*M does not match the matrix%s (%ld)", "", (long)L * M);
+    if (B == 0) return SB_OK;
+    return dense_amp_impl(d, y, Pl, 0.0, beta0, L, M, B, T, beta, iters, n_exec, flags, tau2_trace, nullptr, nullptr, nullptr,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int sb_dense_amp_batch_sharded(sb_dense *d, const double *y, const double *Pl_local, double P_total,
+                                          const double *beta0_local, int L_local, int M, int B, int T, double *beta_local,
+                                          int *iters, int *n_exec, unsigned *flags, double *tau2_trace, double *xbuf,
+                                          sb_allreduce_fn allreduce, void *ctx, void *stream) {
+    if (!d || !y || !Pl_local || !beta_local || !iters || !n_exec || !flags || !xbuf || !allreduce || B < 0 || T < 0 ||
+        L_local <= 0 || M <= 0)
+        return fail(SB_EINVAL, "sb_dense_amp_batch_sharded: bad argument%s", "");
+    if ((long)L_local * M != d->LM)
+        return fail(SB_EINVAL, "sb_dense_amp_batch_sharded: L_local*M does not match the matrix%s (%ld)", "", (long)L_local * M);
+    if (B == 0) return SB_OK;
+    return dense_amp_impl(d, y, Pl_local, P_total, beta0_local, L_local, M, B, T, beta_local, iters, n_exec, flags, tau2_trace,
+                          allreduce, ctx, xbuf, (cudaStream_t)stream);
 }

@@ -226,6 +226,51 @@ class DenseOperator:
         return AmpResult(beta, iters, n_exec, flags, tau2)
 
 
+    def amp_sharded(self, y, Pl_local, P_total, T, allreduce=None, group=None, beta0=None, trace=False):
+        """Column-sharded AMP: this operator holds the columns of the local sections of a larger matrix
+        (sb_dense_amp_batch_sharded).  y [B, n] is replicated; Pl_local / beta0 / the returned beta refer to the
+        local sections; P_total = sum of Pl over all sections.  `allreduce(tensor)` must sum a CUDA float64 tensor
+        in place over the ranks (default: torch.distributed.all_reduce over `group`, i.e. NCCL over NVLink); it is
+        called once per AMP iteration on [B*n + B] doubles (partial A beta and |beta|^2)."""
+        import ctypes as ct
+        _chk(y, F64, "y")
+        _chk(Pl_local, F64, "Pl_local")
+        _chk(beta0, F64, "beta0")
+        B, n = y.shape
+        if n != self.n or Pl_local.numel() != self.L:
+            raise ValueError("y must be [B, n] and Pl_local [L_local]")
+        dev = y.device
+        if allreduce is None:
+            import torch.distributed as dist
+
+            def allreduce(t):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        xbuf = torch.empty(B * n + B, dtype=F64, device=dev)
+        err = []
+
+        def _cb(ctx, buf, count, stream):
+            try:
+                allreduce(xbuf)
+                return 0
+            except Exception as ex:  # never let an exception cross the C ABI
+                err.append(ex)
+                return 1
+
+        cb = ct.CFUNCTYPE(ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_long, ct.c_void_p)(_cb)
+        beta = torch.empty((B, self.L * self.M), dtype=F64, device=dev)
+        iters = torch.empty(B, dtype=I32, device=dev)
+        n_exec = torch.empty(B, dtype=I32, device=dev)
+        flags = torch.empty(B, dtype=I32, device=dev)
+        tau2 = torch.empty((B, max(T, 1)), dtype=F64, device=dev) if trace else None
+        rc = _lib.lib().sb_dense_amp_batch_sharded(self._h, _p(y), _p(Pl_local), float(P_total), _p(beta0), self.L, self.M,
+                                                   B, int(T), _p(beta), _p(iters), _p(n_exec), _p(flags), _p(tau2),
+                                                   _p(xbuf), ct.cast(cb, ct.c_void_p), None, _stream())
+        if err:
+            raise err[0]
+        check(rc, "sb_dense_amp_batch_sharded")
+        return AmpResult(beta, iters, n_exec, flags, tau2)
+
+
 _OP_CACHE = {}
 
 

@@ -247,6 +247,66 @@ def test_gaussian_design_matrix_c1(S, oracle):
     assert Ab(beta[0]).shape == (n, 1) and relinf(Ab(beta[0]).reshape(-1), A @ beta[0]) < 1e-6
 
 
+def test_gaussian_column_sharded_matches_unsharded(Eng, oracle):
+    """Column-sharded dense A (north star: A too large for one GPU): two shards of 64 sections each decode the same
+    batch, exchanging partial A beta and |beta|^2 once per iteration through the allreduce callback of
+    sb_dense_amp_batch_sharded.  Here the two 'ranks' are two host threads on one GPU and the allreduce is a
+    barrier + add (the multi-GPU run uses torch.distributed / NCCL, tools/gaussian_sharded.py); the result must
+    agree with the unsharded decode and with the oracle."""
+    import threading
+    L, M, P, T, n, B = 128, 4, 2.0, 64, 256, 5
+    Pl = P / L * np.ones(L)
+    rs = np.random.RandomState(11)
+    A = rs.randn(n, L * M) / np.sqrt(n)
+    ys = []
+    for b in range(B):
+        b0 = np.zeros(L * M)
+        b0[np.arange(L) * M + rs.randint(0, M, L)] = np.sqrt(n * Pl)
+        ys.append(A @ b0 + 0.6 * rs.randn(n))
+    y = torch.from_numpy(np.array(ys)).cuda()
+    full = Eng.DenseOperator(A, L, M).amp(y, torch.from_numpy(Pl).cuda(), T)
+    Lh = L // 2
+    ops = [Eng.DenseOperator(A[:, r * Lh * M:(r + 1) * Lh * M], Lh, M) for r in range(2)]
+    bufs, out, errs = [None, None], [None, None], []
+    bar = threading.Barrier(2)
+
+    def worker(r):
+        try:
+            torch.cuda.set_device(0)
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                def allreduce(t):
+                    bufs[r] = t
+                    st.synchronize()
+                    bar.wait()
+                    total = bufs[0] + bufs[1]       # both threads compute the same sum, in the same order
+                    st.synchronize()
+                    bar.wait()
+                    t.copy_(total)
+                    st.synchronize()
+                    bar.wait()
+                out[r] = ops[r].amp_sharded(y, torch.from_numpy(Pl[r * Lh:(r + 1) * Lh]).cuda(), P, T, allreduce=allreduce)
+                st.synchronize()
+        except Exception as ex:
+            errs.append(ex)
+            bar.abort()
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join(120) for t in th]
+    assert not errs, errs
+    beta = torch.cat([out[0].beta, out[1].beta], dim=1).cpu().numpy()
+    assert torch.equal(out[0].iters, out[1].iters) and torch.equal(out[0].n_exec, out[1].n_exec)
+    for b in range(B):
+        ref, t = oracle.amp(ys[b].reshape(-1, 1), Pl, L, M, T, lambda v: (A @ np.asarray(v).reshape(-1)).reshape(-1, 1),
+                            lambda v: (A.T @ np.asarray(v).reshape(-1)).reshape(-1, 1))
+        e_ref = relinf(beta[b], ref.reshape(-1))
+        e_full = relinf(beta[b], full.beta[b].cpu().numpy())
+        print("sharded Gaussian codeword %d: rel err vs oracle %.2e, vs unsharded %.2e, iterations %d (unsharded %d, ref %d)"
+              % (b, e_ref, e_full, int(out[0].iters[b]), int(full.iters[b]), t))
+        assert e_ref < NORTH_STAR_RTOL and e_full < NORTH_STAR_RTOL
+
+
 @pytest.mark.parametrize("shape", [(256, 512, 100), (130, 200, 7), (384, 1000, 129), (4608, 2048, 40), (640, 40000, 130)])
 def test_dense_gemm_bf16x3_against_fp64(Eng, shape):
     """The tcgen05 / TMA GEMM of the Gaussian mode alone: A x and A^T x for ragged shapes (rows not a multiple of
