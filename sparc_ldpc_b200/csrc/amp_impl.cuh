@@ -185,23 +185,32 @@ __device__ __forceinline__ int fold16q(const uint4 p0, const uint4 p1, const int
     return s;
 }
 
-// table of one section: [EPT][2*NB][TEAM][8 entries]; the two (2*NB) 16-byte loads of bin e+1 are issued before
-// bin e is reduced when NB == 1 (w/M <= 16, the headline shapes)
-template <int LOGM, bool PRE>
+// table of one section: [EPT][2*NB][TEAM][8 entries].  NBT = 1 | 2 (w/M <= 16 | 32, the headline and the C5
+// shapes): fully unrolled, the two 16-byte loads of the next 16-entry chunk are issued before the current chunk
+// is reduced.  NBT = 0: any NB, plain loop.
+template <int LOGM, bool PRE, int NBT>
 __device__ __forceinline__ void fold_section_q(double (&x)[TeamCfg<LOGM>::EPT], const uint16_t *__restrict__ tab,
                                                int NB, int q, const int *zs, double unit) {
     constexpr int TEAM = TeamCfg<LOGM>::TEAM, EPT = TeamCfg<LOGM>::EPT;
     const uint4 *t4 = reinterpret_cast<const uint4 *>(tab) + q;
-    if (NB == 1) {
+    if (NBT > 0) {
+        constexpr int NCH = EPT * (NBT > 0 ? NBT : 1);  // chunks of 16 entries, bin-major
         uint4 c0 = __ldg(t4), c1 = __ldg(t4 + TEAM);
+        double v = 0.0;
 #pragma unroll
-        for (int e = 0; e < EPT; e++) {
+        for (int i = 0; i < NCH; i++) {
             uint4 n0 = c0, n1 = c1;
-            if (e + 1 < EPT) {
-                n0 = __ldg(t4 + (2 * (e + 1)) * TEAM);
-                n1 = __ldg(t4 + (2 * (e + 1) + 1) * TEAM);
+            if (i + 1 < NCH) {
+                n0 = __ldg(t4 + (2 * (i + 1)) * TEAM);
+                n1 = __ldg(t4 + (2 * (i + 1) + 1) * TEAM);
             }
-            x[e] = (double)fold16q<PRE>(c0, c1, zs) * unit;
+            const int s = fold16q<PRE>(c0, c1, zs);
+            if (NBT == 1) {
+                x[i] = (double)s * unit;
+            } else {
+                v = (i % NBT == 0) ? (double)s : v + (double)s;
+                if (i % NBT == NBT - 1) x[i / NBT] = v * unit;
+            }
             c0 = n0;
             c1 = n1;
         }
@@ -236,7 +245,7 @@ struct SecCtx {  // per-iteration scalars of the section phase
 
 // mode 0: AMP iteration (fold -> FHT -> softmax -> store beta -> FHT -> +-F)
 // mode 1: operator only (load beta -> FHT -> +-F)   [prologue z = y - A beta0, sb_Ab_batch]
-template <int LOGM, bool PRE, bool QUANT>
+template <int LOGM, bool PRE, bool QUANT, int NBT>
 __device__ __forceinline__ void section_phase(int mode, bool first_zero, const AmpArgs &a, const double *bsrc,
                                               double *bdst, int sec, int q, const void *zsv, char *Fbytes, int slot,
                                               const SecCtx &cx, double rt_npl, double &sq, double &gmax, double &lmin) {
@@ -245,10 +254,11 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
     double x[EPT];
     const unsigned tmask = team_mask<TEAM>();
     if (mode == 0) {
-        if (QUANT)
-            fold_section_q<LOGM, PRE>(x, a.invq + ((size_t)sec * M) * a.Hp, a.NB, q, static_cast<const int *>(zsv),
-                                      cx.zunit);
-        else
+        if (QUANT) {
+            const uint16_t *tab = a.invq + ((size_t)sec * M) * a.Hp;
+            const int *zq = static_cast<const int *>(zsv);
+            fold_section_q<LOGM, PRE, NBT>(x, tab, a.NB, q, zq, cx.zunit);
+        } else
             fold_section<LOGM, PRE, double>(x, a.inv + ((size_t)sec * M) * a.Hp, a.Hp, a.NB, q,
                                             static_cast<const double *>(zsv), 1.0);
         fht_team<LOGM>(x, q, tmask);
@@ -485,7 +495,7 @@ __device__ __forceinline__ void gather_phaseq(const uint16_t *__restrict__ fwdq,
 }
 
 // One pass over all active sections: section_phase per team, then the gather per group.
-template <int LOGM, bool PRE, bool QUANT>
+template <int LOGM, bool PRE, bool QUANT, int NBT>
 __device__ __forceinline__ void operator_pass(int mode, bool first_zero, const AmpArgs &a, const double *bsrc,
                                               double *bdst, const int *act, int La, const void *zsv, double *acc_s,
                                               char *Fbytes, int *sec_s, int W, const SecCtx &cx, double nd, double &sq,
@@ -501,7 +511,7 @@ __device__ __forceinline__ void operator_pass(int mode, bool first_zero, const A
         if (q == 0 && tm < W) sec_s[tm] = sec;
         if (valid) {
             const double rt_npl = sqrt(nd * a.Pl[sec]);
-            section_phase<LOGM, PRE, QUANT>(mode, first_zero, a, bsrc ? bsrc + (size_t)sidx * M : nullptr,
+            section_phase<LOGM, PRE, QUANT, NBT>(mode, first_zero, a, bsrc ? bsrc + (size_t)sidx * M : nullptr,
                                             bdst ? bdst + (size_t)sidx * M : nullptr, sec, q, zsv, Fbytes, tm, cx,
                                             rt_npl, sq, gmax, lmin);
         }
@@ -566,7 +576,8 @@ struct Smem {
 // power-of-two ceiling exponent: smallest e with |v| < 2^e  (v > 0 finite)
 __device__ __forceinline__ int ceil_exp(double v) { return (v > 0.0) ? ilogb(v) + 1 : 0; }
 
-template <int LOGM, bool PRE, bool QUANT>
+// NBT: 16-entry chunks per bin of the FAST fold table known at compile time (1 | 2), 0 = read a.NB (and STRICT)
+template <int LOGM, bool PRE, bool QUANT, int NBT>
 __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
     constexpr int M = TeamCfg<LOGM>::M;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -631,7 +642,7 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
             }
             cx.fscale = scalbn(1.0, 27 - ceil_exp(block_max(bound, red) * (1.0 + 1e-6)));
         }
-        operator_pass<LOGM, PRE, QUANT>(1, false, a, b0, beta, act, La, zsv, acc_s, sm.F, sm.sec, W, cx, nd, sq, gmax,
+        operator_pass<LOGM, PRE, QUANT, NBT>(1, false, a, b0, beta, act, La, zsv, acc_s, sm.F, sm.sec, W, cx, nd, sq, gmax,
                                         lmin);
         for (int k = threadIdx.x; k < n; k += blockDim.x) zf[k] = y[k] - acc_s[k] / rt_n;
     } else {
@@ -675,7 +686,7 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
         sq = 0.0;
         gmax = -INFINITY;
         lmin = INFINITY;
-        operator_pass<LOGM, PRE, QUANT>(0, first_zero, a, beta, beta, act, La, zsv, acc_s, sm.F, sm.sec, W, cx, nd, sq,
+        operator_pass<LOGM, PRE, QUANT, NBT>(0, first_zero, a, beta, beta, act, La, zsv, acc_s, sm.F, sm.sec, W, cx, nd, sq,
                                         gmax, lmin);
         first_zero = false;
         const double sumsq = block_sum(sq, red);
@@ -710,7 +721,7 @@ __global__ void __launch_bounds__(512, 1) Ab_kernel(AmpArgs a, int W, const doub
     const double nd = (double)n, rt_n = sqrt(nd);
     SecCtx cx;
     cx.inv_rt_n = 1.0 / rt_n; cx.tau2 = 1.0; cx.zunit = 1.0; cx.fscale = 1.0;
-    operator_pass<LOGM, PRE, false>(1, false, a, beta_in + (size_t)b * a.L * M, nullptr, act, La, sm.zf, sm.acc, sm.F,
+    operator_pass<LOGM, PRE, false, 0>(1, false, a, beta_in + (size_t)b * a.L * M, nullptr, act, La, sm.zf, sm.acc, sm.F,
                                     sm.sec, W, cx, nd, sq, gmax, lmin);
     for (int k = threadIdx.x; k < n; k += blockDim.x) out[(size_t)b * n + k] = sm.acc[k] / rt_n;
 }
@@ -779,10 +790,14 @@ int launch_amp(const sb_operator *op, AmpArgs a, int B, int which, const double 
         KERNEL<<<B, nt, smem, st>>>(__VA_ARGS__);                                                        \
     } while (0)
     if (which == 0 || which == 3) {
-        if (quant && op->qpre) SB_LAUNCH((amp_kernel<LOGM, true, true>), a, W);
-        else if (quant) SB_LAUNCH((amp_kernel<LOGM, false, true>), a, W);
-        else if (op->pre) SB_LAUNCH((amp_kernel<LOGM, true, false>), a, W);
-        else SB_LAUNCH((amp_kernel<LOGM, false, false>), a, W);
+        const int nbt = (op->NB == 1) ? 1 : ((op->NB == 2 && LOGM == 9) ? 2 : 0);
+        if (quant && op->qpre && nbt == 1) SB_LAUNCH((amp_kernel<LOGM, true, true, 1>), a, W);
+        else if (quant && op->qpre) SB_LAUNCH((amp_kernel<LOGM, true, true, 0>), a, W);
+        else if (quant && nbt == 1) SB_LAUNCH((amp_kernel<LOGM, false, true, 1>), a, W);
+        else if (quant && nbt == 2) SB_LAUNCH((amp_kernel<LOGM, false, true, (LOGM == 9 ? 2 : 0)>), a, W);
+        else if (quant) SB_LAUNCH((amp_kernel<LOGM, false, true, 0>), a, W);
+        else if (op->pre) SB_LAUNCH((amp_kernel<LOGM, true, false, 0>), a, W);
+        else SB_LAUNCH((amp_kernel<LOGM, false, false, 0>), a, W);
     } else if (which == 1) {
         if (op->pre) SB_LAUNCH((Ab_kernel<LOGM, true>), a, W, in, out);
         else SB_LAUNCH((Ab_kernel<LOGM, false>), a, W, in, out);

@@ -58,6 +58,24 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// the same box, delivered to the same CTA-relative shared-memory offset (and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -70,6 +88,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrives on the barrier at the same offset in every CTA of `mask` once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -110,7 +133,11 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    double *__restrict__ out, int M, int N, int ldo, long slice_stride, int nkb, int kb_per_slice,
-                   int kb_per_chunk) {
+                   int kb_per_chunk, int CL) {
+    // CL = thread-block cluster size along the row tiles (1 | 2 | 4): the CL CTAs of a cluster work on CL
+    // consecutive 128-row tiles of the A-side operand against the SAME codeword tile and K slice, so each CTA
+    // fetches only BN / CL rows of the codeword-side operand and TMA-multicasts them to all CL CTAs (the kernel
+    // is bound by L2 -> SM traffic: 72 KB per 32-k stage alone, 48 KB with CL = 2, 36 KB with CL = 4).
     using S = GemmSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -125,10 +152,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int m0 = blockIdx.x * GM, n0 = blockIdx.y * BN, slice = blockIdx.z;
     const int kb0 = slice * kb_per_slice, kb1 = min(nkb, kb0 + kb_per_slice);
 
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(full(s), 1);
-            mbar_init(empty(s), 1);
+            mbar_init(empty(s), CL);  // a stage is refilled by every CTA of the cluster: all of them must release it
         }
         mbar_init(tfull, 1);
         mbar_init(tempty, 4);
@@ -139,7 +168,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tslot_ptr;
 
@@ -153,8 +182,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const uint32_t dst = base + s * S::STAGE_BYTES;
 #pragma unroll
                 for (int p = 0; p < 3; p++) tma_load_3d(dst + p * GM * GKB, &tmA, full(s), kb * GK, m0, p);
+                if (CL == 1) {
 #pragma unroll
-                for (int p = 0; p < 3; p++) tma_load_3d(dst + S::A_BYTES + p * BN * GKB, &tmB, full(s), kb * GK, n0, p);
+                    for (int p = 0; p < 3; p++) tma_load_3d(dst + S::A_BYTES + p * BN * GKB, &tmB, full(s), kb * GK, n0, p);
+                } else {  // this CTA's share of the codeword rows, to every CTA of the cluster
+                    const int rows = BN / CL;
+#pragma unroll
+                    for (int p = 0; p < 3; p++)
+                        tma_load_3d_mc(dst + S::A_BYTES + p * BN * GKB + crank * rows * GKB, &tmB, full(s), kb * GK,
+                                       n0 + crank * rows, p, cmask);
+                }
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
@@ -192,7 +229,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         umma_bf16(d_lo, ad[2], bd[0], idesc, 1u);
                         acc = 1u;
                     }
-                    umma_commit(empty(s));  // frees the stage once these MMAs have read it
+                    if (CL == 1) umma_commit(empty(s));  // frees the stage once these MMAs have read it
+                    else umma_commit_mc(empty(s), cmask);
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
                 umma_commit(tfull);  // chunk complete -> epilogue
@@ -235,7 +273,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA leaves while peers may still write to it
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * BN) : "memory");
@@ -536,12 +574,40 @@ static int dense_reserve(sb_dense *d, int B, int L) {
 }
 
 // part[s][b][m] = sum over slice s of Aop[m][k] * xplanes[b][k];  transpose = 0: Aop = A (M = n, K = LM), 1: A^T
+template <int BN, int STAGES>
+static int launch_gemm(dim3 grid, int CL, cudaStream_t st, const CUtensorMap &mapA, const CUtensorMap &mapB, double *part,
+                       int Mrows, int B, long sstride, int nkb, int per, int chunk) {
+    using S = GemmSmem<BN, STAGES>;
+    auto kern = gemm_bf16x3_kernel<BN, STAGES>;
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(192, 1, 1);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SB_CUDA(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, part, Mrows, B, Mrows, sstride, nkb, per, chunk, CL));
+    return SB_OK;
+}
+
 static int dense_gemm_launch(const sb_dense *d, int transpose, const __nv_bfloat16 *xpl, int B, double *part,
                              int *slices_out, long *slice_stride_out, cudaStream_t st) {
     const int Mrows = transpose ? d->LM : d->n, K = transpose ? d->n : d->LM, Kp = transpose ? d->np : d->LMp;
     const int BN = pick_bn(B);
+    const int mtiles = (Mrows + GM - 1) / GM;
+    int CL = 2;  // cluster size: the codeword-side tile is fetched once per cluster (SB_DENSE_CLUSTER = 1 | 2 | 4)
+    if (const char *env = getenv("SB_DENSE_CLUSTER")) CL = atoi(env);
+    if (CL != 1 && CL != 2 && CL != 4) CL = 2;
+    while (CL > 1 && mtiles < CL) CL /= 2;
     CUtensorMap mapB;
-    int rc = make_map(&mapB, xpl, B, K, Kp, BN);
+    int rc = make_map(&mapB, xpl, B, K, Kp, BN / CL);
     if (rc != SB_OK) return rc;
     int slices, per;
     plan_slices(d, Mrows, K, B, BN, &slices, &per);
@@ -549,17 +615,12 @@ static int dense_gemm_launch(const sb_dense *d, int transpose, const __nv_bfloat
     const char *env = getenv("SB_DENSE_CHUNK_KB");
     const int chunk = env ? atoi(env) : 32;
     const long sstride = (long)B * Mrows;
-    dim3 grid((Mrows + GM - 1) / GM, (B + BN - 1) / BN, slices);
+    // row tiles padded to whole clusters: the extra CTAs read zeros (TMA out-of-range fill) and store nothing
+    dim3 grid(((mtiles + CL - 1) / CL) * CL, (B + BN - 1) / BN, slices);
     const CUtensorMap &mapA = transpose ? d->mapAt : d->mapA;
-    if (BN == 256) {
-        using S = GemmSmem<256, 3>;
-        SB_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-        gemm_bf16x3_kernel<256, 3><<<grid, 192, S::TOTAL, st>>>(mapA, mapB, part, Mrows, B, Mrows, sstride, nkb, per, chunk);
-    } else {
-        using S = GemmSmem<128, 4>;
-        SB_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-        gemm_bf16x3_kernel<128, 4><<<grid, 192, S::TOTAL, st>>>(mapA, mapB, part, Mrows, B, Mrows, sstride, nkb, per, chunk);
-    }
+    if (BN == 256) rc = launch_gemm<256, 3>(grid, CL, st, mapA, mapB, part, Mrows, B, sstride, nkb, per, chunk);
+    else rc = launch_gemm<128, 4>(grid, CL, st, mapA, mapB, part, Mrows, B, sstride, nkb, per, chunk);
+    if (rc != SB_OK) return rc;
     SB_LAUNCHED();
     *slices_out = slices;
     *slice_stride_out = sstride;
