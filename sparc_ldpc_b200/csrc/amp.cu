@@ -85,6 +85,11 @@ struct FastTables {
 
 static int team_lanes(int M) { return M >= 128 ? 32 : (M >= 4 ? M / 4 : 1); }
 
+// bin held by register e of lane q after the fold: M = 512 uses the transposed layout B of amp_impl.cuh
+static int fast_bin(int logM, int TEAM, int e, int q) {
+    return logM == 9 ? (q >> 1) * 32 + 2 * e + (q & 1) : e * TEAM + q;
+}
+
 static void parallel_for(int count, const std::function<void(int, int)> &body) {
     int nt = (int)std::thread::hardware_concurrency();
     if (nt < 1) nt = 1;
@@ -134,7 +139,7 @@ static void build_fast_tables(const uint32_t *ordering, int L, int M, int n, int
             for (int e = 0; e < EPT; e++) {
                 E.clear();
                 for (int q = 0; q < TEAM; q++)
-                    for (int o : bins[e * TEAM + q]) E.push_back(PoolEdge{q, o & 31, o, 0});
+                    for (int o : bins[fast_bin(logM, TEAM, e, q)]) E.push_back(PoolEdge{q, o & 31, o, 0});
                 ps.run(E, Hp);
                 PoolScheduler::improve(E, Hp);
                 stat[(size_t)l * 2] += Hp;
@@ -182,7 +187,7 @@ static void build_fast_tables(const uint32_t *ordering, int L, int M, int n, int
                         const uint32_t r = ordering[(size_t)(g * PW + i) * n + k0 + q];
                         const uint32_t lo = r % M, sg = __builtin_popcount(r / M) & 1;
                         const uint32_t off = (uint32_t)(i / SPR) * (2u << SBQ) + (uint32_t)(i % SPR) * ((uint32_t)M << 2) +
-                                             (lo << 2) + (sg << SBQ);
+                                             (fq_word(logM, lo) << 2) + (sg << SBQ);
                         E.push_back(PoolEdge{q, (int)((off >> 2) & 31), (int)off, 0});
                     }
                 ps.run(E, PW);
@@ -292,9 +297,10 @@ extern "C" int sb_fast_tables_check(const uint32_t *ordering, int L, int M, int 
     std::vector<int> seen(n);
     for (int l = 0; l < L; l++) {
         std::fill(seen.begin(), seen.end(), 0);
-        for (int j = 0; j < M; j++)
+        for (int eq = 0; eq < M; eq++)
             for (int t = 0; t < Hp; t++) {
-                const int o = ft.invq[((((size_t)l * EPT + j / TEAM) * NH + (t >> 3)) * TEAM + j % TEAM) * 8 + (t & 7)] >> osh;
+                const int j = fast_bin(logM, TEAM, eq / TEAM, eq % TEAM);
+                const int o = ft.invq[((((size_t)l * EPT + eq / TEAM) * NH + (t >> 3)) * TEAM + eq % TEAM) * 8 + (t & 7)] >> osh;
                 if (o >= n && o < n + 32) continue;  // zero word
                 const int neg = o >= ft.qneg, k = neg ? o - ft.qneg : o;
                 if (k < 0 || k >= n) return fail(SB_EINVAL, "fast tables: fold offset out of range%s (%ld)", "", o);
@@ -311,7 +317,8 @@ extern "C" int sb_fast_tables_check(const uint32_t *ordering, int L, int M, int 
                 const uint32_t off = ft.fwdq[(((size_t)g * (PW / 8) + (t >> 3)) * n + k) * 8 + (t & 7)];
                 const uint32_t region = off / (2u << SBQ), in = off % (2u << SBQ);
                 const uint32_t sg = in >> SBQ, rest = in & ((1u << SBQ) - 1), slot = region * 8 + rest / ((uint32_t)M << 2);
-                const uint32_t lo = (rest % ((uint32_t)M << 2)) >> 2;
+                uint32_t lo = (rest % ((uint32_t)M << 2)) >> 2;
+                if (logM == 9) lo = ((lo >> 1) & 15u) * 32u + 2u * (lo >> 5) + (lo & 1u);  // inverse of fq_word
                 if (slot >= (uint32_t)PW || (off & 3)) return fail(SB_EINVAL, "fast tables: bad gather offset%s (%ld)", "", off);
                 const uint32_t r = ordering[(size_t)(g * PW + slot) * n + k];
                 if (r % M != lo || (uint32_t)(__builtin_popcount(r / M) & 1) != sg)

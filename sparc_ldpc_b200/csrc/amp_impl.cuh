@@ -90,6 +90,78 @@ __device__ __forceinline__ void fht_team(double (&x)[TeamCfg<LOGM>::EPT], int q,
     }
 }
 
+// ---- FAST mode, M = 512: transforms with ONE shuffle stage ----------------------------------------------------
+// Two register layouts of the 512 values of a section held by a warp (lane q, register index i):
+//   layout A: j = i * 32 + q                              (coalesced beta access; registers = bits 8..5 of j)
+//   layout B: j = (q >> 1) * 32 + 2 * i + (q & 1)         (registers = bits 4..1 of j, lane bit 0 = bit 0 of j)
+// A transform = 4 register stages in one layout, a transpose through the warp's own (still unused) +-F slot in
+// shared memory, 4 register stages in the other layout, and one xor-1 shuffle stage for bit 0 of j: 96
+// shared-memory wavefronts instead of the 160 of five shuffle stages, and ~150 fewer instructions.
+// Staging position of element (row = j >> 5, col = j & 31), in doubles: row * 32 + (col ^ 2 row), rows 0..7 in
+// the +F half of the slot and rows 8..15 in the -F half; the xor keeps both access patterns conflict-free.
+__device__ __forceinline__ double *stage_at(int *Fp, int *Fn, int row, int col) {
+    double *base = reinterpret_cast<double *>(row < 8 ? Fp : Fn);
+    return base + (row & 7) * 32 + (col ^ ((2 * row) & 31));
+}
+
+__device__ __forceinline__ void reg_stages16(double (&x)[16]) {
+#pragma unroll
+    for (int s = 8; s >= 1; s >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if ((i & s) == 0) {
+                const double a = x[i], b = x[i + s];
+                x[i] = a + b;
+                x[i + s] = a - b;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void shuffle_stage1(double (&x)[16], int q) {
+    const int sgn = (q & 1) ? (int)0x80000000 : 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const double p = __shfl_xor_sync(0xffffffffu, x[i], 1);
+        const double mine = __hiloint2double(__double2hiint(x[i]) ^ sgn, __double2loint(x[i]));
+        x[i] = p + mine;
+    }
+}
+
+// layout B in, layout A out; stage order 16, 8, 4, 2, 1, 256, 128, 64, 32 (exact for the integer-valued fold)
+__device__ __forceinline__ void fht512_B_to_A(double (&x)[16], int q, int *Fp, int *Fn) {
+    reg_stages16(x);
+    shuffle_stage1(x, q);
+    const int a = q >> 1, b = q & 1;
+#pragma unroll
+    for (int i = 0; i < 16; i++) *stage_at(Fp, Fn, a, 2 * i + b) = x[i];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = *stage_at(Fp, Fn, i, q);
+    __syncwarp();
+    reg_stages16(x);
+}
+
+// layout A in, layout B out; stage order 256, ..., 2, 1 = the reference's (ldpc/sparc_ldpc.py:19-29)
+__device__ __forceinline__ void fht512_A_to_B(double (&x)[16], int q, int *Fp, int *Fn) {
+    reg_stages16(x);
+#pragma unroll
+    for (int i = 0; i < 16; i++) *stage_at(Fp, Fn, i, q) = x[i];
+    __syncwarp();
+    const int a = q >> 1, b = q & 1;
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = *stage_at(Fp, Fn, a, 2 * i + b);
+    __syncwarp();
+    reg_stages16(x);
+    shuffle_stage1(x, q);
+}
+
+// physical word of F_l[lo] inside its +-F copy (FAST mode, M = 512): the transform ends in layout B, and
+// p(lo) = ((lo >> 1) & 15) * 32 + (lo >> 5) * 2 + (lo & 1) makes the store of register i a contiguous 128 bytes
+__host__ __device__ __forceinline__ uint32_t fq_word(int logM, uint32_t lo) {
+    return logM == 9 ? (((lo >> 1) & 15u) * 32u + (lo >> 5) * 2u + (lo & 1u)) : lo;
+}
+
 // z value addressed by an inverse-table entry e.  PRE: e = k*4 (byte offset of an int32), else e = k.
 template <bool PRE, typename T>
 __device__ __forceinline__ T zs_at(const T *zs, uint32_t e) {
@@ -251,17 +323,21 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
                                               const SecCtx &cx, double rt_npl, double &sq, double &gmax, double &lmin) {
     constexpr int M = TeamCfg<LOGM>::M, TEAM = TeamCfg<LOGM>::TEAM, EPT = TeamCfg<LOGM>::EPT;
     constexpr int SBQ = TeamCfg<LOGM>::SBQ;
+    constexpr bool TRQ = QUANT && LOGM == 9;  // transposed transforms (one shuffle stage), F stored at fq_word()
     double x[EPT];
     const unsigned tmask = team_mask<TEAM>();
+    int *Fqp = reinterpret_cast<int *>(Fbytes + slot_offset<LOGM, 2>(slot));
+    int *Fqn = reinterpret_cast<int *>(Fbytes + slot_offset<LOGM, 2>(slot) + (1 << SBQ));
     if (mode == 0) {
-        if (QUANT) {
+        if (QUANT) {  // (for M = 512 the table lists the bins in layout B)
             const uint16_t *tab = a.invq + ((size_t)sec * M) * a.Hp;
             const int *zq = static_cast<const int *>(zsv);
             fold_section_q<LOGM, PRE, NBT>(x, tab, a.NB, q, zq, cx.zunit);
         } else
             fold_section<LOGM, PRE, double>(x, a.inv + ((size_t)sec * M) * a.Hp, a.Hp, a.NB, q,
                                             static_cast<const double *>(zsv), 1.0);
-        fht_team<LOGM>(x, q, tmask);
+        if constexpr (TRQ) fht512_B_to_A(x, q, Fqp, Fqn);
+        else fht_team<LOGM>(x, q, tmask);
         const double c2 = rt_npl / cx.tau2;
         double m = -INFINITY;
 #pragma unroll
@@ -297,10 +373,19 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
             if (bdst != nullptr) bdst[e * TEAM + q] = x[e];
         }
     }
+    if constexpr (TRQ) {
+        fht512_A_to_B(x, q, Fqp, Fqn);
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {  // register e of lane q holds lo = (q>>1)*32 + 2e + (q&1): word e*32 + q
+            const int f = __double2int_rn(x[e] * cx.fscale);
+            Fqp[e * 32 + q] = f;
+            Fqn[e * 32 + q] = -f;
+        }
+        return;
+    }
     fht_team<LOGM>(x, q, tmask);
     if (QUANT) {
-        int *Fp = reinterpret_cast<int *>(Fbytes + slot_offset<LOGM, 2>(slot));
-        int *Fn = reinterpret_cast<int *>(Fbytes + slot_offset<LOGM, 2>(slot) + (1 << SBQ));
+        int *Fp = Fqp, *Fn = Fqn;
 #pragma unroll
         for (int e = 0; e < EPT; e++) {
             const int f = __double2int_rn(x[e] * cx.fscale);
@@ -327,10 +412,19 @@ __device__ __forceinline__ T F_at(const char *slot_base, uint32_t e) {
 // acc[k] += sum over the group's sections (ascending) of sgn * F[lo]     (sparc_ldpc.py:123-126, :70)
 // generic section lists: one u16 row per section.  T = double (strict) or int (fixed point, flushed to fp64
 // every 16 sections so that the int32 partial sums cannot overflow).
+// fwd entry (lo*4 | sgn << SBQ) -> offset of the signed F word in the layout of the FAST M = 512 slot
+template <int LOGM>
+__device__ __forceinline__ uint32_t fq_entry(uint32_t e) {
+    constexpr int SBQ = TeamCfg<LOGM>::SBQ;
+    if (LOGM != 9) return e;
+    return (fq_word(9, (e & ((1u << SBQ) - 1u)) >> 2) << 2) | (e & (1u << SBQ));
+}
+
 template <int LOGM, typename T>
 __device__ __forceinline__ void gather_phase(const uint16_t *__restrict__ fwd, int n, int nvalid, const int *sec_s,
                                              const char *Fbytes, double *acc_s, double funit, int first = 0) {
     constexpr int ESH = sizeof(T) == 8 ? 3 : 2;
+    constexpr bool REMAP = sizeof(T) == 4 && LOGM == 9;
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
         double acc = acc_s[k];
         T part = 0;
@@ -338,7 +432,10 @@ __device__ __forceinline__ void gather_phase(const uint16_t *__restrict__ fwd, i
         for (; tm + 4 <= nvalid; tm += 4) {
             uint32_t e[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) e[i] = __ldg(fwd + (size_t)sec_s[tm + i] * n + k);
+            for (int i = 0; i < 4; i++) {
+                e[i] = __ldg(fwd + (size_t)sec_s[tm + i] * n + k);
+                if (REMAP) e[i] = fq_entry<LOGM>(e[i]);
+            }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const T v = F_at<T>(Fbytes + slot_offset<LOGM, ESH>(tm + i), e[i]);
@@ -350,7 +447,9 @@ __device__ __forceinline__ void gather_phase(const uint16_t *__restrict__ fwd, i
             }
         }
         for (; tm < nvalid; tm++) {
-            const T v = F_at<T>(Fbytes + slot_offset<LOGM, ESH>(tm), __ldg(fwd + (size_t)sec_s[tm] * n + k));
+            uint32_t e1 = __ldg(fwd + (size_t)sec_s[tm] * n + k);
+            if (REMAP) e1 = fq_entry<LOGM>(e1);
+            const T v = F_at<T>(Fbytes + slot_offset<LOGM, ESH>(tm), e1);
             if (sizeof(T) == 8) acc += v; else part += v;
         }
         if (sizeof(T) != 8) acc += (double)part * funit;
@@ -526,7 +625,7 @@ __device__ __forceinline__ void operator_pass(int mode, bool first_zero, const A
                 else gather_phaseq<LOGM, 16>(a.fwdq, a.n, g0, nch, Fbytes, acc_s, funit);
                 if (nch * a.PW < nvalid)
                     gather_phase<LOGM, int>(a.fwd, a.n, nvalid, sec_s, Fbytes, acc_s, funit, nch * a.PW);
-            } else if (fast) gather_phase8<LOGM, int>(a.fwd8, a.n, g0, nvalid, Fbytes, acc_s, funit);
+            } else if (fast && LOGM != 9) gather_phase8<LOGM, int>(a.fwd8, a.n, g0, nvalid, Fbytes, acc_s, funit);
             else gather_phase<LOGM, int>(a.fwd, a.n, nvalid, sec_s, Fbytes, acc_s, funit);
         } else {
             if (fast) gather_phase8<LOGM, double>(a.fwd8, a.n, g0, nvalid, Fbytes, acc_s, 1.0);
