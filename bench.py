@@ -349,7 +349,7 @@ def gpu_arm(args):
                          "kernel_busy_fraction_of_timed_region": amp_ms / ms,
                          "avg_launch_ms": amp_ms / max(n_amp_launch, 1),
                          "algorithmic_bytes_per_launch": alg_bytes / max(n_amp_launch, 1),
-                         "co_limiter": "LSU / shared-memory data pipe 61% busy, issue 46%, fp64 18%: phases run one pipe at a time (profiles/r01_amp_kernel_ncu_full.csv v7; bank-conflict replays removed by scheduled tables)"},
+                         "co_limiter": "latency-bound at 16 warps/SM: LSU data pipe 63% busy, issue 43%, fp64 21%; top stalls long-scoreboard 21% (L2 table loads), fp64 dependency 17%, LSU queue 15% (profiles/r01_amp_kernel_ncu_full.csv v9)"},
             "clocks": clocks.summary(),
         }
         if world == 1 and not args.no_cpu:
