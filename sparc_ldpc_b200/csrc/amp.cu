@@ -339,6 +339,17 @@ static AmpArgs base_args(const sb_operator *op, const int *sections, const int *
     return a;
 }
 
+#ifdef SB_PHASE_CLOCKS
+static unsigned long long *g_dbg = nullptr;
+// experiment builds only: read (and clear) the per-phase cycle counters of the AMP kernel
+extern "C" int sb_phase_cycles_read(unsigned long long *out16) {
+    if (!g_dbg) { memset(out16, 0, 16 * sizeof(unsigned long long)); return SB_OK; }
+    SB_CUDA(cudaMemcpy(out16, g_dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    SB_CUDA(cudaMemset(g_dbg, 0, 16 * sizeof(unsigned long long)));
+    return SB_OK;
+}
+#endif
+
 extern "C" int sb_amp_batch(const sb_operator *op, const double *y, const double *Pl, const double *beta0,
                             const int *sections, const int *nsec, int B, int T, int mode, double *beta, int *iters,
                             int *n_exec, unsigned *flags, double *tau2_trace, double *scratch, void *stream) {
@@ -352,6 +363,10 @@ extern "C" int sb_amp_batch(const sb_operator *op, const double *y, const double
     a.zscratch = scratch;
     a.y = y; a.Pl = Pl; a.beta0 = beta0; a.beta = beta; a.tau2_trace = tau2_trace;
     a.iters = iters; a.n_exec = n_exec; a.flags = flags; a.T = T;
+#ifdef SB_PHASE_CLOCKS
+    if (!g_dbg) { SB_CUDA(cudaMalloc(&g_dbg, 16 * sizeof(unsigned long long))); SB_CUDA(cudaMemset(g_dbg, 0, 16 * sizeof(unsigned long long))); }
+    a.dbg = g_dbg;
+#endif
     return dispatch(op, a, B, mode == SB_AMP_FAST ? 3 : 0, nullptr, nullptr, (cudaStream_t)stream);
 }
 

@@ -309,7 +309,29 @@ struct AmpArgs {
     int *iters, *n_exec;
     unsigned *flags;
     int L, n, Hp, NB, T;
+#ifdef SB_PHASE_CLOCKS
+    unsigned long long *dbg;  // experiment builds only: cycles per phase, accumulated by thread 0 of every CTA
+#endif
 };
+
+// Experiment builds (make EXTRA=-DSB_PHASE_CLOCKS, tools/phase_clocks.py): thread 0 adds the cycles since its
+// previous mark to dbg[i].
+#ifdef SB_PHASE_CLOCKS
+__device__ __forceinline__ unsigned &sb_clk_last() {
+    __shared__ unsigned last;
+    return last;
+}
+#define SB_CLK(a, i)                                                             \
+    do {                                                                         \
+        if (threadIdx.x == 0) {                                                  \
+            const unsigned c__ = (unsigned)clock();                              \
+            atomicAdd((a).dbg + (i), (unsigned long long)(c__ - sb_clk_last())); \
+            sb_clk_last() = c__;                                                 \
+        }                                                                        \
+    } while (0)
+#else
+#define SB_CLK(a, i) do { } while (0)
+#endif
 
 struct SecCtx {  // per-iteration scalars of the section phase
     double inv_rt_n, tau2, zunit, fscale;
@@ -336,6 +358,7 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
         } else
             fold_section<LOGM, PRE, double>(x, a.inv + ((size_t)sec * M) * a.Hp, a.Hp, a.NB, q,
                                             static_cast<const double *>(zsv), 1.0);
+        SB_CLK(a, 1);
         // beta_l streams from HBM: FAST issues its loads before the first transform, which hides their latency
         // (issuing them before the fold as well costs the fold its registers: 3.27 vs 3.09 us measured)
         double bv[TRQ ? EPT : 1];
@@ -346,6 +369,7 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
         } else {
             fht_team<LOGM>(x, q, tmask);
         }
+        SB_CLK(a, 2);
         const double c2 = rt_npl / cx.tau2;
         double m = -INFINITY;
 #pragma unroll
@@ -376,6 +400,7 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
             sq += x[e] * x[e];
             bdst[e * TEAM + q] = x[e];
         }
+        SB_CLK(a, 3);
     } else {
 #pragma unroll
         for (int e = 0; e < EPT; e++) {
@@ -391,6 +416,7 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
             Fqp[e * 32 + q] = f;
             Fqn[e * 32 + q] = -f;
         }
+        SB_CLK(a, 4);
         return;
     }
     fht_team<LOGM>(x, q, tmask);
@@ -604,27 +630,35 @@ __device__ __forceinline__ void gather_phaseq(const uint16_t *__restrict__ fwdq,
 }
 
 // One pass over all active sections: section_phase per team, then the gather per group.
+// Measured and rejected on this structure (tools/ab_build.sh, tools/profile_amp.py; 2.94 us per codeword-iteration
+// as is): the first gather-table loads of a group issued before the barrier that publishes F (3.26 us), the row
+// batches of the gather software-pipelined through two register buffers (spills, 4.7 us), a second +-F area with
+// one barrier per group instead of two (3.31 us), the beta loads moved behind the first transform's transpose (3.09
+// us), the second transform in 32-bit fixed point (3.20 us), a deeper table prefetch in the fold (neutral).  The
+// kernel sits at the 128-register limit; each of these adds live state that ptxas pays for elsewhere.
 template <int LOGM, bool PRE, bool QUANT, int NBT>
 __device__ __forceinline__ void operator_pass(int mode, bool first_zero, const AmpArgs &a, const double *bsrc,
                                               double *bdst, const int *act, int La, const void *zsv, double *acc_s,
-                                              char *Fbytes, int *sec_s, int W, const SecCtx &cx, double nd, double &sq,
+                                              char *Fbytes, int *sec_s, int W, const SecCtx &cx, const double *rtp, double &sq,
                                               double &gmax, double &lmin) {
     constexpr int M = TeamCfg<LOGM>::M, TEAM = TeamCfg<LOGM>::TEAM;
     const int tm = threadIdx.x / TEAM, q = threadIdx.x % TEAM;
     const bool qpass = QUANT;
     for (int k = threadIdx.x; k < a.n; k += blockDim.x) acc_s[k] = 0.0;
     for (int g0 = 0; g0 < La; g0 += W) {
+        SB_CLK(a, 0);
         const int sidx = g0 + tm;
         const bool valid = (tm < W) && (sidx < La);
         const int sec = valid ? (act ? act[sidx] : sidx) : 0;
         if (q == 0 && tm < W) sec_s[tm] = sec;
         if (valid) {
-            const double rt_npl = sqrt(nd * a.Pl[sec]);
+            const double rt_npl = (mode == 0) ? rtp[sidx] : 0.0;
             section_phase<LOGM, PRE, QUANT, NBT>(mode, first_zero, a, bsrc ? bsrc + (size_t)sidx * M : nullptr,
                                             bdst ? bdst + (size_t)sidx * M : nullptr, sec, q, zsv, Fbytes, tm, cx,
                                             rt_npl, sq, gmax, lmin);
         }
         __syncthreads();
+        SB_CLK(a, 5);
         const int nvalid = min(W, La - g0);
         const bool fast = (act == nullptr && (W & 7) == 0);
         const double funit = 1.0 / cx.fscale;
@@ -641,7 +675,9 @@ __device__ __forceinline__ void operator_pass(int mode, bool first_zero, const A
             if (fast) gather_phase8<LOGM, double>(a.fwd8, a.n, g0, nvalid, Fbytes, acc_s, 1.0);
             else gather_phase<LOGM, double>(a.fwd, a.n, nvalid, sec_s, Fbytes, acc_s, 1.0);
         }
+        SB_CLK(a, 6);
         __syncthreads();
+        SB_CLK(a, 7);
     }
 }
 
@@ -694,6 +730,9 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
     Smem<LOGM, QUANT> sm(smem_raw, n, W);
     double *zf = QUANT ? a.zscratch + (size_t)b * n : sm.zf;  // every thread only touches its own k = tid + j*NT
     double *acc_s = sm.acc, *red = sm.red;
+    // sqrt(n P_l) of the i-th active section, staged once behind the other arrays (a per-section global load and
+    // sqrt at the top of every section stalled the warp: 2.4 % of the stall samples)
+    double *rtp = reinterpret_cast<double *>(smem_raw + ((Smem<LOGM, QUANT>::bytes(n, W) + 7) & ~(size_t)7));
     if (QUANT) {
         if (threadIdx.x < 32) sm.zq[n + threadIdx.x] = 0;  // one zero word per bank
     } else if (threadIdx.x == 0) {
@@ -729,6 +768,7 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
         const double p = a.Pl[act ? act[i] : i];
         pl += p;
         plmax = fmax(plmax, p);
+        rtp[i] = sqrt(nd * p);
     }
     const double P = block_sum(pl, red);
     const double cmax = sqrt(nd * block_max(plmax, red));
@@ -751,7 +791,7 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
             }
             cx.fscale = scalbn(1.0, 27 - ceil_exp(block_max(bound, red) * (1.0 + 1e-6)));
         }
-        operator_pass<LOGM, PRE, QUANT, NBT>(1, false, a, b0, beta, act, La, zsv, acc_s, sm.F, sm.sec, W, cx, nd, sq, gmax,
+        operator_pass<LOGM, PRE, QUANT, NBT>(1, false, a, b0, beta, act, La, zsv, acc_s, sm.F, sm.sec, W, cx, rtp, sq, gmax,
                                         lmin);
         for (int k = threadIdx.x; k < n; k += blockDim.x) zf[k] = y[k] - acc_s[k] / rt_n;
     } else {
@@ -795,7 +835,8 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
         sq = 0.0;
         gmax = -INFINITY;
         lmin = INFINITY;
-        operator_pass<LOGM, PRE, QUANT, NBT>(0, first_zero, a, beta, beta, act, La, zsv, acc_s, sm.F, sm.sec, W, cx, nd, sq,
+        SB_CLK(a, 8);
+        operator_pass<LOGM, PRE, QUANT, NBT>(0, first_zero, a, beta, beta, act, La, zsv, acc_s, sm.F, sm.sec, W, cx, rtp, sq,
                                         gmax, lmin);
         first_zero = false;
         const double sumsq = block_sum(sq, red);
@@ -805,6 +846,7 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
         const double ons = P - sumsq / nd;  // (:220)
         for (int k = threadIdx.x; k < n; k += blockDim.x) zf[k] = (y[k] - acc_s[k] / rt_n) + (zf[k] / cx.tau2) * ons;
         __syncthreads();
+        SB_CLK(a, 9);
         executed++;
     }
     if (first_zero) {  // T == 0 or stop before the first update: beta is the zero vector
@@ -831,7 +873,7 @@ __global__ void __launch_bounds__(512, 1) Ab_kernel(AmpArgs a, int W, const doub
     SecCtx cx;
     cx.inv_rt_n = 1.0 / rt_n; cx.tau2 = 1.0; cx.zunit = 1.0; cx.fscale = 1.0;
     operator_pass<LOGM, PRE, false, 0>(1, false, a, beta_in + (size_t)b * a.L * M, nullptr, act, La, sm.zf, sm.acc, sm.F,
-                                    sm.sec, W, cx, nd, sq, gmax, lmin);
+                                    sm.sec, W, cx, nullptr, sq, gmax, lmin);
     for (int k = threadIdx.x; k < n; k += blockDim.x) out[(size_t)b * n + k] = sm.acc[k] / rt_n;
 }
 
@@ -878,9 +920,9 @@ static int pick_threads(int n, int L, int pw, size_t *smem_out, int *W_out) {
     if (nt < 32) nt = 32;
     if (nt < TEAM) nt = TEAM;
     while (nt > 64 && (nt / 2) / TEAM >= L) nt /= 2;
-    while (nt > 32 && nt > TEAM && Smem<LOGM, QUANT>::bytes(n, nt / TEAM) > 227 * 1024) nt /= 2;
+    while (nt > 32 && nt > TEAM && Smem<LOGM, QUANT>::bytes(n, nt / TEAM) + 8 * (size_t)L + 8 > 227 * 1024) nt /= 2;
     *W_out = nt / TEAM;
-    *smem_out = Smem<LOGM, QUANT>::bytes(n, *W_out);
+    *smem_out = ((Smem<LOGM, QUANT>::bytes(n, *W_out) + 7) & ~(size_t)7) + sizeof(double) * (size_t)L;  // + rtp[L]
     return nt;
 }
 
