@@ -16,6 +16,8 @@ and the only collective is the NCCL all-reduce of the error counters.
 own c_ldpc.c when oracle/_ref was built) on all host cores, one codeword per worker per step.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -349,7 +351,7 @@ def gpu_arm(args):
                          "kernel_busy_fraction_of_timed_region": amp_ms / ms,
                          "avg_launch_ms": amp_ms / max(n_amp_launch, 1),
                          "algorithmic_bytes_per_launch": alg_bytes / max(n_amp_launch, 1),
-                         "co_limiter": "latency-bound at 16 warps/SM: LSU data pipe 63% busy, issue 43%, fp64 21%; top stalls long-scoreboard 21% (L2 table loads), fp64 dependency 17%, LSU queue 15% (profiles/r01_amp_kernel_ncu_full.csv v9)"},
+                         "co_limiter": "not HBM: the L1 data pipe (2 L n random shared-memory reads + 25 KB of L2-resident table words per section) is 66% busy, issue 45%, fp64 21%; stalls: long-scoreboard 18% (table loads), MIO queue 17%, barrier 7% (profiles/r01_amp_kernel_ncu_full.csv v10, r01_amp_phase_clocks.txt)"},
             "clocks": clocks.summary(),
         }
         if world == 1 and not args.no_cpu:
@@ -380,10 +382,25 @@ def main():
                     help="AMP arithmetic: strict = fp64 in the reference's add order; fast = fp64 with 32-bit "
                          "fixed-point gathers (include/sparc_b200.h SB_AMP_FAST); both pass the parity tests")
     args = ap.parse_args()
-    if args.impl == "reference":
-        reference_arm(args)
-    else:
-        gpu_arm(args)
+    # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version banner under
+    # torchrun, for one) is sent to stderr, and the real stdout is restored for the result line only
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        if args.impl == "reference":
+            reference_arm(args)
+        else:
+            gpu_arm(args)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+    lines = [ln for ln in out.getvalue().splitlines() if ln.strip()]
+    for ln in lines[:-1]:
+        print(ln, file=sys.stderr)
+    if lines:
+        print(lines[-1], flush=True)
 
 
 if __name__ == "__main__":
