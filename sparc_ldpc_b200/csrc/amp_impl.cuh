@@ -739,6 +739,9 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
         zf[n] = 0.0;
     }
     const void *zsv = QUANT ? static_cast<const void *>(sm.zq) : static_cast<const void *>(zf);
+#ifdef SB_PHASE_CLOCKS
+    if (threadIdx.x == 0) sb_clk_last() = (unsigned)clock();  // (the first mark of a CTA would otherwise add garbage)
+#endif
 
     const int La = a.nsec ? a.nsec[b] : a.L;
     const int *act = a.sections ? a.sections + (size_t)b * a.L : nullptr;

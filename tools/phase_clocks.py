@@ -15,7 +15,7 @@ sp = S.SPARCParams(L=512, M=512, sigma=0.9964, p=4.0, r=1, t=T)
 su = D.make_setup(sp, S.LDPCParams("802.16", "5/6", 192))
 idx, noise = S._draw(su, B, 0.9964, np.random.RandomState(0))
 tx, y = S._transmit(su, idx, noise)
-lib = ct.CDLL(_lib.LIB_PATH)
+lib = ct.CDLL(_lib.LIB_PATH)  # SPARC_B200_LIB selects the experiment build
 out = (ct.c_ulonglong * 16)()
 names = ["other", "fold", "fht1", "softmax+store", "fht2+F", "wait1", "gather", "wait2", "tau+quant", "zupdate"]
 for rep in range(3):
