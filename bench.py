@@ -162,6 +162,7 @@ def gpu_arm(args):
 
     B = args.batch
     E.AMP_MODE = args.amp_mode
+    E.BP_MODE = args.bp_mode
     sp = S.SPARCParams(L=L, M=M, sigma=SIGMA, p=P, r=R_SPARC, t=T)
     su = D.make_setup(sp, S.LDPCParams(STD, RATE, Z))
     assert su.n == N and su.total_bits - (su.nl - su.kl) == INFO_BITS
@@ -336,6 +337,8 @@ def gpu_arm(args):
             "config": {"workload": WORKLOAD, "codewords_per_step_per_gpu": B, "sigma": SIGMA, "amp_T": T, "streams": S_,
                        "amp_mode": args.amp_mode + (" (fp64; z and FHT(beta) gathered from 27-bit fixed-point copies)"
                                                     if args.amp_mode == "fast" else " (fp64, reference add order)"),
+                       "bp_mode": args.bp_mode + (" (fp64 messages; the two log(1+exp(-|x|)) terms of every Lxor in single precision)"
+                                                  if args.bp_mode == "fast" else " (fp64 exp/log as c_ldpc.c:246-247)"),
                        "l2": "working set %.0f MB of beta per GPU per step exceeds the 126 MB L2" % (B * L * M * 8 / 1e6),
                        "ber_per_stage[amp1,ldpc1,amp2,ldpc2,amp3]": (errs_tot / nbits).tolist(),
                        "mean_amp_iterations_per_decode": exec_iters / (3.0 * total_cw),
@@ -381,6 +384,9 @@ def main():
     ap.add_argument("--amp-mode", default="fast", choices=["strict", "fast"],
                     help="AMP arithmetic: strict = fp64 in the reference's add order; fast = fp64 with 32-bit "
                          "fixed-point gathers (include/sparc_b200.h SB_AMP_FAST); both pass the parity tests")
+    ap.add_argument("--bp-mode", default="fast", choices=["strict", "fast"],
+                    help="sum-product check nodes: strict = fp64 exp/log; fast = single-precision Lxor correction "
+                         "terms (SB_BP_SUMPROD2_FAST); decisions of convergent blocks are identical (tests)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version banner under
     # torchrun, for one) is sent to stderr, and the real stdout is restored for the result line only

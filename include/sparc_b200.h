@@ -42,6 +42,10 @@ extern "C" {
 #define SB_BP_SUMPROD2 0 /* c_ldpc.c:138-206 (default of ldpc.py:855)  */
 #define SB_BP_SUMPROD 1  /* c_ldpc.c:32-113  (tanh / atanh rule)        */
 #define SB_BP_MINSUM 2   /* c_ldpc.c:339-381 (without the :364 indexing bug) */
+#define SB_BP_SUMPROD2_FAST 3 /* sumprod2 with the two log(1+exp(-|x|)) correction terms of every Lxor
+                                 (c_ldpc.c:246-247) evaluated in single precision; sign-min term, variable-node
+                                 sums, app and the stop test in fp64.  app agrees with SB_BP_SUMPROD2 to ~1e-6,
+                                 iteration counts and hard decisions are equal except for near-ties */
 
 /* per-codeword status bits written by sb_amp_batch into flags[b] */
 #define SB_AMP_STOPPED 1u   /* tau == last_tau fired (sparc_ldpc.py:204)                        */

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SPARC_B200_LIB: another build of the same library (kernel A/B experiments, tools/ab_build.sh)
 LIB_PATH = os.environ.get("SPARC_B200_LIB") or os.path.join(_HERE, "libsparc_b200.so")
 
-SB_BP_SUMPROD2, SB_BP_SUMPROD, SB_BP_MINSUM = 0, 1, 2
+SB_BP_SUMPROD2, SB_BP_SUMPROD, SB_BP_MINSUM, SB_BP_SUMPROD2_FAST = 0, 1, 2, 3
 SB_AMP_STOPPED, SB_AMP_REF_NAN = 1, 2
 SB_AMP_STRICT, SB_AMP_FAST = 0, 1
 SB_MAX_ITCOUNT = 200

@@ -27,6 +27,24 @@ __host__ __device__ __forceinline__ double lxor(double L1, double L2, int corr) 
     return L;
 }
 
+// FAST rule (SB_BP_SUMPROD2_FAST): the same node update with the two correction terms log(1 + exp(-|x|)) of every
+// Lxor evaluated in single precision (ex2 / lg2 special-function units) and added to the fp64 sign-min term.  The
+// terms are bounded by ln 2, so the absolute error per Lxor is ~1e-7; messages, variable-node sums, app and the
+// stop test stay fp64.  ~8 fp64-pipe instructions per Lxor instead of ~90 (2 exp + 2 log in fp64).
+__device__ __forceinline__ double lxor_fast(double L1, double L2) {
+    double L = (signbit(L1) == signbit(L2)) ? 1.0 : -1.0;
+    L *= fmin(fabs(L1), fabs(L2));
+    const float s = (float)fabs(L1 + L2), d = (float)fabs(L1 - L2);
+    const float c = __logf(1.0f + __expf(-s)) - __logf(1.0f + __expf(-d));
+    return L + (double)c;
+}
+
+template <int RULE>
+__device__ __forceinline__ double lxor_rule(double L1, double L2) {
+    if (RULE == SB_BP_SUMPROD2_FAST) return lxor_fast(L1, L2);
+    return lxor(L1, L2, RULE == SB_BP_SUMPROD2);
+}
+
 struct BpArgs {
     const int *voff, *vpos, *cbase, *cstride, *cdeg;
     const double *ch;
@@ -60,14 +78,14 @@ __device__ __forceinline__ double check_fb(double *msg, int base, int stride, in
 // check fits (768 threads at the headline code instead of 384 with two checks each), and twice as many warps
 // hide the exp / log latency.  Operands and their order are those of check_fb, i.e. of Lxfb
 // (c_ldpc.c:294-314): results are bit-identical.
-template <int DCMAX>
-__device__ __forceinline__ double check_fb_reg(double *msg, int base, int stride, int dc, int corr) {
+template <int RULE, int DCMAX>
+__device__ __forceinline__ double check_fb_reg(double *msg, int base, int stride, int dc) {
     double bs[DCMAX];
     double bk = msg[base + (dc - 1) * stride];
     bs[dc - 1] = bk;
 #pragma unroll 1
     for (int k = dc - 2; k >= 0; k--) {
-        bk = lxor(bk, msg[base + k * stride], corr);  // b[k] = Lxor(b[k+1], L[k])      (:305)
+        bk = lxor_rule<RULE>(bk, msg[base + k * stride]);  // b[k] = Lxor(b[k+1], L[k])      (:305)
         bs[k] = bk;
     }
     double f = msg[base];
@@ -75,8 +93,8 @@ __device__ __forceinline__ double check_fb_reg(double *msg, int base, int stride
 #pragma unroll 1
     for (int k = 1; k < dc - 1; k++) {
         const double Lk = msg[base + k * stride];
-        msg[base + k * stride] = lxor(f, bs[k + 1], corr);  // L[k] = Lxor(f[k-1], b[k+1])   (:311)
-        f = lxor(f, Lk, corr);                              // f[k] = Lxor(f[k-1], L[k])      (:303)
+        msg[base + k * stride] = lxor_rule<RULE>(f, bs[k + 1]);  // L[k] = Lxor(f[k-1], b[k+1])   (:311)
+        f = lxor_rule<RULE>(f, Lk);                              // f[k] = Lxor(f[k-1], L[k])      (:303)
     }
     msg[base + (dc - 1) * stride] = f;  // L[dc-1] = f[dc-2]
     return bk;                          // b[0]
@@ -107,7 +125,7 @@ __global__ void __launch_bounds__(768, 1) bp_kernel_reg(BpArgs a) {
         int unsat = 0;
         for (int c = tid; c < a.Nc; c += NT) {
             const int dc = a.cdeg[c], base = a.cbase[c], stride = a.cstride[c];
-            const double tot = check_fb_reg<DCMAX>(msg, base, stride, dc, RULE == SB_BP_SUMPROD2);
+            const double tot = check_fb_reg<RULE, DCMAX>(msg, base, stride, dc);
             if (tot <= 0.0) unsat = 1;  // c_ldpc.c:191
             if (RULE == SB_BP_MINSUM)
                 for (int k = 0; k < dc; k++) msg[base + k * stride] *= a.factor;  // :370-371
@@ -256,6 +274,7 @@ extern "C" int sb_bp_batch(const sb_graph *g, int rule, const double *ch, int B,
     // local-array variant (no shared-memory scratch): one thread per check, up to 768; SB_BP_SCRATCH=1 forces the scratch variant
     const size_t msgb = sizeof(double) * (size_t)g->Nmsg;
     const bool reg_ok = rule != SB_BP_SUMPROD && g->dcmax <= 24 && msgb <= 227 * 1024 && !getenv("SB_BP_SCRATCH");
+    if (rule == SB_BP_SUMPROD2_FAST && !reg_ok) rule = SB_BP_SUMPROD2;  // the scratch-column kernel has no FAST variant
     if (reg_ok) {
         int ntr = ((g->Nc + 31) / 32) * 32;
         if (ntr > 768) {  // several checks per thread: balanced passes (768 threads = 85 registers each)
@@ -274,6 +293,7 @@ extern "C" int sb_bp_batch(const sb_graph *g, int rule, const double *ch, int B,
         else SB_REG(r, 24);                             \
     } while (0)
         if (rule == SB_BP_SUMPROD2) SB_REG_DC(SB_BP_SUMPROD2);
+        else if (rule == SB_BP_SUMPROD2_FAST) SB_REG_DC(SB_BP_SUMPROD2_FAST);
         else if (rule == SB_BP_MINSUM) SB_REG_DC(SB_BP_MINSUM);
         else return fail(SB_EINVAL, "sb_bp_batch: unknown rule%s %ld", "", rule);
 #undef SB_REG_DC

@@ -11,13 +11,17 @@ from . import _lib
 from ._lib import check
 
 F64, I32 = torch.float64, torch.int32
-_RULES = {"sumprod2": _lib.SB_BP_SUMPROD2, "sumprod": _lib.SB_BP_SUMPROD, "minsum": _lib.SB_BP_MINSUM}
+_RULES = {"sumprod2": _lib.SB_BP_SUMPROD2, "sumprod": _lib.SB_BP_SUMPROD, "minsum": _lib.SB_BP_MINSUM,
+          "sumprod2_fast": _lib.SB_BP_SUMPROD2_FAST}
 _MODES = {"strict": _lib.SB_AMP_STRICT, "fast": _lib.SB_AMP_FAST}
 # Default arithmetic of Operator.amp.  "strict" = fp64 in the reference's order of additions (parity mode);
 # "fast" = 32-bit fixed-point gathers.  Override per call with mode=..., or globally
 # with the environment variable SPARC_B200_AMP_MODE.
 import os as _os
 AMP_MODE = _os.environ.get("SPARC_B200_AMP_MODE", "strict")
+# Default arithmetic of Graph.bp for dectype "sumprod2": "strict" = fp64 exp/log as c_ldpc.c:246-247; "fast" = the
+# Lxor correction terms in single precision (SB_BP_SUMPROD2_FAST).  Environment: SPARC_B200_BP_MODE.
+BP_MODE = _os.environ.get("SPARC_B200_BP_MODE", "strict")
 
 
 def _dev():
@@ -317,7 +321,8 @@ class Graph:
             raise NameError("Channel inputs not consistent with variable degrees")
         app = torch.empty_like(ch)
         it = torch.empty(B, dtype=I32, device=ch.device)
-        check(_lib.lib().sb_bp_batch(self._h, _RULES[dectype], _p(ch), B, _p(app), _p(it), int(max_it),
+        rule = _RULES["sumprod2_fast"] if (dectype == "sumprod2" and BP_MODE == "fast") else _RULES[dectype]
+        check(_lib.lib().sb_bp_batch(self._h, rule, _p(ch), B, _p(app), _p(it), int(max_it),
                                      float(corr_factor), _stream()), "sb_bp_batch")
         return app, it
 

@@ -515,6 +515,77 @@ def test_bp_matches_oracle_on_fresh_noise(oracle):
             np.testing.assert_allclose(app[b], ao, rtol=1e-9, atol=1e-9)
 
 
+def test_bp_fast_rule_against_strict(Eng):
+    """SB_BP_SUMPROD2_FAST (single-precision Lxor correction terms): on blocks that converge the iteration count and
+    the hard decisions equal those of the fp64 rule and app agrees to 1e-5; saturated / erased inputs
+    (+-DBL_MAX, 0: the AMP handoff's classes, sparc_ldpc.py:667-669) are handled identically."""
+    from sparc_ldpc_b200 import ldpc
+    c = ldpc.code("802.16", "5/6", 192)
+    rs = np.random.RandomState(21)
+    X = c.encode_batch(rs.randint(0, 2, (96, c.K)))
+    for s, min_ok in ((0.50, 96), (0.54, 80)):
+        ch = 2 / s ** 2 * (1 - 2.0 * X + s * rs.randn(*X.shape))
+        ch[:, ::97] = 0.0                                                 # erasures
+        big = np.where(X[:, 5::101] > 0, -np.finfo(np.float64).max, np.finfo(np.float64).max)
+        ch[:, 5::101] = big                                               # saturated, correct sign
+        g = c.graph()
+        a0, i0 = g.bp(cu(ch), "sumprod2")
+        a1, i1 = g.bp(cu(ch), "sumprod2_fast")
+        a0, i0, a1, i1 = a0.cpu().numpy(), i0.cpu().numpy(), a1.cpu().numpy(), i1.cpu().numpy()
+        conv = (i0 < 200) & (i1 < 200)
+        assert conv.sum() >= min_ok
+        # blocks that converge quickly take exactly the same number of iterations; slow ones (tens of iterations
+        # spent near an unstable orbit) amplify the 1e-7 perturbation and may stop an iteration or two apart,
+        # at the same codeword
+        quick = conv & (i0 <= 25)
+        print("BP fast vs strict, sigma %.2f: %d converged (%d quick), iteration counts differ on %d"
+              % (s, conv.sum(), quick.sum(), int((i0[conv] != i1[conv]).sum())))
+        assert np.array_equal(i0[quick], i1[quick])
+        assert (i0[conv] != i1[conv]).mean() < 0.05
+        assert np.array_equal(a0[conv] < 0, a1[conv] < 0)
+        def rel_err(mask):
+            fin = np.isfinite(a0[mask]) & (np.abs(a0[mask]) < 1e300)
+            return np.abs(a1[mask][fin] - a0[mask][fin]) / (1 + np.abs(a0[mask][fin]))
+        eq, es = rel_err(quick), rel_err(conv & (i0 == i1))
+        print("   app error, relative: quick blocks max %.2e, all blocks median %.2e max %.2e" % (eq.max(), np.median(es), es.max()))
+        assert eq.max() < 2e-5 and np.median(es) < 1e-6 and es.max() < 1e-2
+    # the engine-wide switch routes dectype "sumprod2" to the fast rule
+    import pytest as _pt
+    mp = _pt.MonkeyPatch()
+    try:
+        mp.setattr(Eng, "BP_MODE", "fast")
+        a2, i2 = g.bp(cu(ch))
+        assert np.array_equal(a2.cpu().numpy(), a1) and np.array_equal(i2.cpu().numpy(), i1)
+    finally:
+        mp.undo()
+
+
+@pytest.mark.parametrize("case", [c for c in FLOW_CASES if c[3] is not None], ids=[c[0] for c in FLOW_CASES if c[3] is not None])
+def test_link_sims_fast_bp(S, Eng, case, monkeypatch):
+    """The golden link-sim BER rows with FAST AMP *and* FAST BP (the bench configuration): unchanged, except on
+    chaotic (non-convergent) BP blocks."""
+    tag, fn, spk, lpk, kw, reps = case
+    monkeypatch.setattr(Eng, "AMP_MODE", "fast")
+    monkeypatch.setattr(Eng, "BP_MODE", "fast")
+    g = golden("flows_small")
+    np.random.seed(int(g[tag + "_seed"]))
+    sp, lp = S.SPARCParams(**spk), S.LDPCParams(*lpk)
+    rows = []
+    for _ in range(reps):
+        if fn == "amp_ldpc_sim":
+            res = S.amp_ldpc_sim(sp, lp)
+        elif fn == "soft_amp_ldpc_sim":
+            res = S.soft_amp_ldpc_sim(sp, lp, kw["soft_iter"])
+        elif fn == "hardinitbeta_amp_ldpc_sim":
+            res = S.hardinitbeta_amp_ldpc_sim(sp, lp)
+        else:
+            res = S.soft_amp_ldpc_hardinit(sp, lp, kw["soft_iter"], kw["threshold"])
+        rows.append(flat_result(res))
+    rows, ref = np.array(rows), g[tag + "_res"]
+    chaotic = (g[tag + "_its"] >= 200).any(axis=1) if g[tag + "_its"].size else np.zeros(reps, dtype=bool)
+    np.testing.assert_array_equal(rows[~chaotic], ref[~chaotic])
+
+
 # ------------------------------------------------------------------------------------------- link simulations
 @pytest.mark.parametrize("case", FLOW_CASES, ids=[c[0] for c in FLOW_CASES])
 def test_link_sims_against_reference(S, case):

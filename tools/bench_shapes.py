@@ -23,6 +23,7 @@ ap.add_argument("--batch", type=int, default=1184)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--only", default="")
 ap.add_argument("--amp-mode", default="fast")
+ap.add_argument("--bp-mode", default="fast")
 args = ap.parse_args()
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -32,6 +33,7 @@ if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 E.AMP_MODE = args.amp_mode
+E.BP_MODE = args.bp_mode
 try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
@@ -94,6 +96,6 @@ for name, (L, M, r, P, lp, flow, kw, db, note) in SHAPES.items():
             "amp_iterations_per_codeword": its / (B * world), "us_per_codeword_iteration": 1e3 * ms * world / max(its, 1),
             "algorithmic_GBps_per_gpu": its / world * bytes_it / (ms / 1e3) / 1e9,
             "frac_of_measured_hbm": its / world * bytes_it / (ms / 1e3) / 1e9 / PEAK,
-            "final_ber": errs / (B * world * su.total_bits), "amp_mode": args.amp_mode}))
+            "final_ber": errs / (B * world * su.total_bits), "amp_mode": args.amp_mode, "bp_mode": args.bp_mode}))
 if world > 1:
     dist.destroy_process_group()

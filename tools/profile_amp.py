@@ -17,6 +17,7 @@ ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--sigma", type=float, default=0.9964)
 ap.add_argument("--bp", action="store_true")
 ap.add_argument("--mode", default="fast")
+ap.add_argument("--bp-rule", default="sumprod2")
 args = ap.parse_args()
 
 sp = S.SPARCParams(L=512, M=512, sigma=args.sigma, p=4.0, r=1, t=args.T)
@@ -40,7 +41,7 @@ if args.bp:
     for i in range(2):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        app, itb = su.graph.bp(llr)
+        app, itb = su.graph.bp(llr, args.bp_rule)
         e1.record()
         torch.cuda.synchronize()
         print("bp launch %d: %.2f ms, %d iterations total" % (i, e0.elapsed_time(e1), int(itb.sum())))
