@@ -52,6 +52,62 @@ __global__ void sp2bp_llr_kernel(const double *__restrict__ beta, long beta_stri
     }
 }
 
+// The same map for M >= 64 with every lane busy.  The sequential ascending-j chain of one (section, bit) pair cannot
+// be split without changing the rounding, so the parallelism comes from the pairs: a CTA stages R sections in
+// shared memory (row stride M + 1 doubles: the rows of a bit group hit distinct bank pairs), then R lanes run
+// the chains of one bit of the R sections, 32 / R bits per warp.  The
+// one-warp-per-section kernel above keeps 9 of 32 lanes busy in its chain phase (1.2 TB/s at M = 512).
+template <int R>  // sections per CTA (8 | 16): lanes r + R g of warp w run the chains of bit w (32 / R) + g
+__global__ void sp2bp_llr_kernel16(const double *__restrict__ beta, long beta_stride, int beta_first,
+                                   const int *__restrict__ sections, const int *__restrict__ nsec, int L_stride,
+                                   int first_sec, int out_first, int count, int M, int logM, int n,
+                                   const double *__restrict__ Pl, double *__restrict__ p_out, double *__restrict__ llr,
+                                   long out_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s = reinterpret_cast<double *>(smem_raw);
+    constexpr int G = 32 / R;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwl = blockDim.x >> 5, nw = (logM + G - 1) / G;
+    const int b = blockIdx.y;
+    const int cnt = sections ? nsec[b] : count;
+    const int i0 = blockIdx.x * R;
+    if (i0 >= cnt) return;
+    const int rows = min(R, cnt - i0), rs = M + 1;
+    for (int r = warp; r < rows; r += nwl) {  // all 8 warps load (enough bytes in flight for HBM); nw of them run chains
+        const int sec = sections ? sections[(size_t)b * L_stride + i0 + r] : first_sec + i0 + r;
+        const double scale = sqrt((double)n * Pl[sec]);  // np.sqrt(n*np.repeat(Pl, M))   (sparc_ldpc.py:657)
+        const double *src = beta + (size_t)b * beta_stride + (size_t)(beta_first + i0 + r) * M;
+        for (int j0 = 0; j0 < M; j0 += 512) {  // 16 loads in flight per lane, then the divisions (whose slow-path
+            double v[16];                        // branches would otherwise serialise load -> divide -> store)
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int j = j0 + 32 * k + lane;
+                v[k] = (j < M) ? src[j] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int j = j0 + 32 * k + lane;
+                if (j < M) s[r * rs + j] = v[k] / scale;
+            }
+        }
+    }
+    __syncthreads();
+    const int r = lane % R, logi = warp * G + lane / R;
+    if (warp >= nw || r >= rows || logi >= logM) return;
+    const double *row = s + r * rs;
+    double acc = 0.0;
+    const int lowmask = (1 << logi) - 1;
+#pragma unroll 8
+    for (int t = 0; t < M / 2; t++) {  // ascending j over the indices whose bit `logi` is set (:276-280)
+        const int j = ((t >> logi) << (logi + 1)) | (1 << logi) | (t & lowmask);
+        acc = acc + row[j];
+    }
+    const int sec = sections ? sections[(size_t)b * L_stride + i0 + r] : first_sec + i0 + r;
+    const int osec = sections ? sec : out_first + i0 + r;
+    const size_t pos = (size_t)b * out_stride + (size_t)osec * logM + (logM - logi - 1);
+    if (p_out) p_out[pos] = acc;
+    llr[pos] = nan_to_num(log(1 - acc) - log(acc));
+}
+
 // numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src) of a[0..n), n a power of two <= 128,
 // executed by one thread.
 __device__ __forceinline__ double np_block_sum(const double *a, int n) {
@@ -123,6 +179,72 @@ __global__ void bp2sp_prior_kernel(const double *__restrict__ app, int ls, const
     for (int m = lane; m < M; m += 32) {
         const double post = s[m] / tot;
         dst[m] = scale_by_power ? post * scale : post;
+    }
+}
+
+// M = 512 with every lane busy in the section sum.  numpy's pairwise sum of 512 values = 4 leaves of 128, each
+// leaf 8 interleaved accumulators of 16 sequential terms (r[j] += a[i + j], i = 8, 16, ...), then
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) per leaf and (l0+l1)+(l2+l3): lane 8 f + j runs accumulator j of leaf f
+// (32 chains of 16 terms; the leaves are staggered by 0, 8, 8, 16 doubles so that a half-warp's 16 lanes hit 16
+// distinct bank pairs), the two trees are xor-shuffles 1, 2, 4 and 8, 16.  Same operands in the same order as
+// bp2sp_prior_kernel, hence the same bits; the bit posteriors are shuffled once per section, not once per product.
+__global__ void bp2sp_prior_kernel512(const double *__restrict__ app, int ls, const double *__restrict__ beta_prev, int L,
+                                      int n, const double *__restrict__ Pl, int scale_by_power, int input_is_prob,
+                                      double *__restrict__ out) {
+    constexpr int M = 512, logM = 9;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    double *s = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (M + 16);
+    const int b = blockIdx.y;
+    const int l = blockIdx.x * wpb + warp;
+    if (l >= L) return;
+    const double scale = sqrt((double)n * Pl[l]);
+    double *dst = out + ((size_t)b * L + l) * M;
+    if (l < L - ls) {  // unprotected section: posterior = beta/scale, prior = posterior*scale (:657, :696)
+        const double *src = beta_prev + ((size_t)b * L + l) * M;
+#pragma unroll 4
+        for (int j = lane; j < M; j += 32) {
+            const double post = src[j] / scale;
+            dst[j] = scale_by_power ? post * scale : post;
+        }
+        return;
+    }
+    double v = 0.0;  // bitwise = 1/(1+exp(app))  (:685), one per lane
+    if (lane < logM) {
+        const double in = app[(size_t)b * ls * logM + (size_t)(l - (L - ls)) * logM + lane];
+        v = input_is_prob ? in : 1 / (1 + exp(in));
+    }
+    double vb[logM], nb[logM];
+#pragma unroll
+    for (int jb = 0; jb < logM; jb++) {
+        vb[jb] = __shfl_sync(0xffffffffu, v, jb);
+        nb[jb] = 1 - vb[jb];
+    }
+    double x[M / 32];
+#pragma unroll
+    for (int k = 0; k < M / 32; k++) {  // np.prod over the logM bits, MSB first (:301-312)
+        const int m = 32 * k + lane;
+        double prod = 1.0;
+#pragma unroll
+        for (int jb = 0; jb < logM; jb++) prod = prod * (((m >> (logM - 1 - jb)) & 1) ? vb[jb] : nb[jb]);
+        x[k] = prod;
+        s[m + 8 * (((m >> 7) + 1) >> 1)] = prod;  // leaf f starts 8 ((f + 1) >> 1) doubles further: bank pairs 0, 8, 8, 0
+    }
+    __syncwarp();
+    const int f = lane >> 3, j = lane & 7;
+    const double *leaf = s + 128 * f + 8 * ((f + 1) >> 1) + j;
+    double r = leaf[0];
+#pragma unroll
+    for (int i = 8; i < 128; i += 8) r += leaf[i];
+    r = r + __shfl_xor_sync(0xffffffffu, r, 1);
+    r = r + __shfl_xor_sync(0xffffffffu, r, 2);
+    r = r + __shfl_xor_sync(0xffffffffu, r, 4);
+    r = r + __shfl_xor_sync(0xffffffffu, r, 8);
+    const double tot = r + __shfl_xor_sync(0xffffffffu, r, 16);
+#pragma unroll
+    for (int k = 0; k < M / 32; k++) {
+        const double post = x[k] / tot;
+        dst[32 * k + lane] = scale_by_power ? post * scale : post;
     }
 }
 
@@ -327,6 +449,33 @@ extern "C" int sb_sp2bp_llr_batch(const double *beta, long beta_stride, int beta
     if ((sections == nullptr) != (nsec == nullptr)) return fail(SB_EINVAL, "sb_sp2bp_llr_batch: sections and nsec go together%s", "");
     const int maxcount = sections ? L_stride : count;
     if (B == 0 || maxcount <= 0) return SB_OK;
+    if (M >= 64 && !getenv("SB_HANDOFF_V1")) {  // 16 sections per CTA, one lane per (section, bit) chain
+        const int logM = ilog2(M);
+        const int R = getenv("SB_SP2BP_R") ? atoi(getenv("SB_SP2BP_R")) : 8;  // 8 measured best (1.26 ms vs 1.54 at 16, 1.38 at 4; 2.03 one warp per section)
+        dim3 grid16((maxcount + R - 1) / R, B);
+        const size_t smem16 = sizeof(double) * R * (size_t)(M + 1);
+        if (R == 4) {
+            if (smem16 > 48 * 1024)
+                SB_CUDA(cudaFuncSetAttribute(sp2bp_llr_kernel16<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+            sp2bp_llr_kernel16<4><<<grid16, 64, smem16, (cudaStream_t)stream>>>(beta, beta_stride, beta_first, sections, nsec,
+                                                                             L_stride, first_sec, out_first, count, M,
+                                                                             logM, n, Pl, p, llr, out_stride);
+        } else if (R == 8) {
+            if (smem16 > 48 * 1024)
+                SB_CUDA(cudaFuncSetAttribute(sp2bp_llr_kernel16<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+            sp2bp_llr_kernel16<8><<<grid16, 128, smem16, (cudaStream_t)stream>>>(beta, beta_stride, beta_first, sections, nsec,
+                                                                              L_stride, first_sec, out_first, count, M,
+                                                                              logM, n, Pl, p, llr, out_stride);
+        } else {
+            if (smem16 > 48 * 1024)
+                SB_CUDA(cudaFuncSetAttribute(sp2bp_llr_kernel16<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+            sp2bp_llr_kernel16<16><<<grid16, 256, smem16, (cudaStream_t)stream>>>(beta, beta_stride, beta_first, sections, nsec,
+                                                                               L_stride, first_sec, out_first, count, M,
+                                                                               logM, n, Pl, p, llr, out_stride);
+        }
+        SB_LAUNCHED();
+        return SB_OK;
+    }
     const int wpb = 8;
     dim3 grid((maxcount + wpb - 1) / wpb, B);
     const size_t smem = sizeof(double) * (size_t)wpb * M;
@@ -351,8 +500,13 @@ extern "C" int sb_bp2sp_prior_batch(const double *app, int ls, const double *bet
     const size_t smem = sizeof(double) * (size_t)wpb * (M + 16);
     if (smem > 48 * 1024)
         SB_CUDA(cudaFuncSetAttribute(bp2sp_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bp2sp_prior_kernel<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(app, ls, beta_prev, L, M, ilog2(M), n, Pl,
-                                                                      scale_by_power, input_is_prob, beta_init);
+    if (M == 512 && !getenv("SB_HANDOFF_V1")) {
+        SB_CUDA(cudaFuncSetAttribute(bp2sp_prior_kernel512, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bp2sp_prior_kernel512<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(app, ls, beta_prev, L, n, Pl, scale_by_power,
+                                                                             input_is_prob, beta_init);
+    } else
+        bp2sp_prior_kernel<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(app, ls, beta_prev, L, M, ilog2(M), n, Pl,
+                                                                          scale_by_power, input_is_prob, beta_init);
     SB_LAUNCHED();
     return SB_OK;
 }
