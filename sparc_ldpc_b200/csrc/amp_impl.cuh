@@ -636,6 +636,11 @@ __device__ __forceinline__ void gather_phaseq(const uint16_t *__restrict__ fwdq,
 // one barrier per group instead of two (3.31 us), the beta loads moved behind the first transform's transpose (3.09
 // us), the second transform in 32-bit fixed point (3.20 us), a deeper table prefetch in the fold (neutral).  The
 // kernel sits at the 128-register limit; each of these adds live state that ptxas pays for elsewhere.
+// Also rejected: beta through per-warp TMA staging rows (cp.async.bulk + mbarrier; correct, 32 registers freed, HBM
+// latency off the warp) -- 3.47 us, because the extra 64 KB of shared memory pushes the carve-out from 164 to 228 KB
+// and the kernel needs its L1: the table loads in flight (16 x 512 bytes per warp) live in L1 line buffers.  The
+// same kernel at carve-out 196 / 228 KB (32 KB / no L1) runs at 3.33 us instead of 2.94; 96 KB of L1 instead of 64
+// brings < 1 % (SB_AMP_CARVEOUT experiments).  This is also why two CTAs per SM (176 KB) lost.
 template <int LOGM, bool PRE, bool QUANT, int NBT>
 __device__ __forceinline__ void operator_pass(int mode, bool first_zero, const AmpArgs &a, const double *bsrc,
                                               double *bdst, const int *act, int La, const void *zsv, double *acc_s,

@@ -17,10 +17,11 @@ ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--sigma", type=float, default=0.9964)
 ap.add_argument("--bp", action="store_true")
 ap.add_argument("--mode", default="fast")
+ap.add_argument("--r", type=float, default=1.0, help="SPARC rate (n = L logM / r)")
 ap.add_argument("--bp-rule", default="sumprod2")
 args = ap.parse_args()
 
-sp = S.SPARCParams(L=512, M=512, sigma=args.sigma, p=4.0, r=1, t=args.T)
+sp = S.SPARCParams(L=512, M=512, sigma=args.sigma, p=4.0, r=args.r, t=args.T)
 su = D.make_setup(sp, S.LDPCParams("802.16", "5/6", 192))
 idx, noise = S._draw(su, args.batch, args.sigma, np.random.RandomState(0))
 tx, y = S._transmit(su, idx, noise)
@@ -34,7 +35,7 @@ for i in range(args.launches):
     it = float(res.n_exec.sum())
     ms = e0.elapsed_time(e1)
     print("amp launch %d: %.2f ms, %d codeword-iterations, %.2f us per codeword-iteration, %.1f GB/s algorithmic"
-          % (i, ms, it, 1e3 * ms / it, it * (2 * 512 * 512 + 3 * 4608) * 8 / ms / 1e6))
+          % (i, ms, it, 1e3 * ms / it, it * (2 * 512 * 512 + 3 * su.n) * 8 / ms / 1e6))
 if args.bp:
     from sparc_ldpc_b200 import engine as E
     llr = E.sp2bp_llr(res.beta, 512, su.n, su.Pl_dev, count=512)
