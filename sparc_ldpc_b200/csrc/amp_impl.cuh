@@ -641,6 +641,9 @@ __device__ __forceinline__ void gather_phaseq(const uint16_t *__restrict__ fwdq,
 // and the kernel needs its L1: the table loads in flight (16 x 512 bytes per warp) live in L1 line buffers.  The
 // same kernel at carve-out 196 / 228 KB (32 KB / no L1) runs at 3.33 us instead of 2.94; 96 KB of L1 instead of 64
 // brings < 1 % (SB_AMP_CARVEOUT experiments).  This is also why two CTAs per SM (176 KB) lost.
+// Gather with the two table halves of a row batch refilled for the next batch as soon as each is consumed (same 24
+// registers, order forced through a run-time-zero data dependency because ptxas sinks the refills): 2.92 us --
+// the waits it removes were not on the critical path, the phase is bound by the L1 data pipe.
 template <int LOGM, bool PRE, bool QUANT, int NBT>
 __device__ __forceinline__ void operator_pass(int mode, bool first_zero, const AmpArgs &a, const double *bsrc,
                                               double *bdst, const int *act, int La, const void *zsv, double *acc_s,
