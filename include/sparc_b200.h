@@ -185,6 +185,27 @@ int sb_dense_amp_batch_sharded(sb_dense *d, const double *y, const double *Pl_lo
                                int *n_exec, unsigned *flags, double *tau2_trace, double *xbuf, sb_allreduce_fn allreduce,
                                void *ctx, void *stream);
 
+/* The same column-sharded decode with the exchange done over NVLink PEER MEMORY instead of a collective library:
+ * every rank owns a receive area of 2 * world * (B*n + B) doubles and `world` 64-bit flag words (zero-initialised),
+ * both mapped by all peers (CUDA IPC across processes, plain pointers inside one process).  Per iteration one kernel
+ * folds the K slices of this rank's partial A beta and pushes it, with |beta|^2, into slot `rank` of every peer's
+ * area; the last CTA publishes the epoch in every peer's flag word (system-scope release); the residual kernel adds
+ * the slots in rank order after all local flags have arrived, so z stays bit-identical on every rank.
+ * slots[r] / flags[r]: rank r's area / flag words AS MAPPED IN THIS PROCESS (r = rank: the local ones).
+ * *epoch_io: exchange counter, 0 before the first call, carried from call to call (all ranks make the same calls).
+ * timeout_ms: a peer that does not arrive in time makes the call fail with SB_ECUDA instead of hanging. */
+#define SB_P2P_MAX 8
+typedef struct {
+    int rank, world, timeout_ms;
+    double *slots[SB_P2P_MAX];
+    unsigned long long *flags[SB_P2P_MAX];
+} sb_p2p;
+int sb_enable_peer_access(int peer_device); /* cudaDeviceEnablePeerAccess from the current device */
+int sb_dense_amp_batch_p2p(sb_dense *d, const double *y, const double *Pl_local, double P_total,
+                           const double *beta0_local, int L_local, int M, int B, int T, double *beta_local, int *iters,
+                           int *n_exec, unsigned *flags, double *tau2_trace, double *xbuf, const sb_p2p *peers,
+                           unsigned long long *epoch_io, void *stream);
+
 /* idx[b][i] = argmax of section i of beta[b] (first maximum wins, sparc_ldpc.py:640-643) */
 int sb_argmax_batch(const double *beta, long beta_stride, int count, int M, int B, int *idx, long idx_stride,
                     void *stream);

@@ -50,6 +50,8 @@ SIGNATURES = {
     "sb_dense_apply_batch": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "sb_dense_amp_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_dense_amp_batch_sharded": (_i, [_vp, _vp, _vp, _d, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_enable_peer_access": (_i, [_i]),
+    "sb_dense_amp_batch_p2p": (_i, [_vp, _vp, _vp, _d, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_argmax_batch": (_i, [_vp, _l, _i, _i, _i, _vp, _l, _vp]),
     "sb_llr2idx_batch": (_i, [_vp, _l, _i, _i, _i, _vp, _l, _vp]),
     "sb_count_errors_batch": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

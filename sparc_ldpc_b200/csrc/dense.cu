@@ -346,6 +346,67 @@ __global__ void dense_sumsq_kernel(const double *__restrict__ secsq, int L, cons
     if (threadIdx.x == 0) out[b] = v;
 }
 
+// ---- column-sharded A over NVLink peer memory (no NCCL in the loop) ------------------------------------------------
+// Every rank owns a receive area [2 parities][world slots][B n + B] doubles that all peers have mapped.  One kernel
+// folds the K slices of this rank's partial A beta, appends its |beta|^2 and PUSHES the result into slot `rank` of
+// every peer's area with plain stores over NVLink (the transfer overlaps the fold tile by tile); the last CTA to
+// finish publishes `epoch` in every peer's flag word with a system-scope release.  A one-warp kernel then waits until
+// all `world` local flags have reached the epoch, and the residual kernel adds the slots in rank order -- the same
+// order on every rank, so z and tau stay bit-identical everywhere and all ranks take the same early exit.  Areas
+// alternate with the parity of the epoch: a rank can run at most one exchange ahead of the slowest reader.
+struct P2pDev {
+    double *slots[SB_P2P_MAX];
+    unsigned long long *flags[SB_P2P_MAX];
+};
+
+__global__ void p2p_push_kernel(const double *__restrict__ part, int slices, long slice_stride, const double *__restrict__ tail,
+                                int n, int B, P2pDev pd, int rank, int world, long area_off, long S,
+                                unsigned long long epoch, unsigned int *__restrict__ done) {
+    const int b = blockIdx.y;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int s = 0; s < slices; s++) acc += part[(size_t)s * slice_stride + (size_t)b * n + m];
+        for (int r = 0; r < world; r++) pd.slots[r][area_off + (size_t)rank * S + (size_t)b * n + m] = acc;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double t = tail ? tail[b] : 0.0;
+        for (int r = 0; r < world; r++) pd.slots[r][area_off + (size_t)rank * S + (size_t)B * n + b] = t;
+    }
+    __threadfence_system();  // this thread's peer stores are performed before the CTA is counted as done
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int total = gridDim.x * gridDim.y;
+        if (atomicAdd(done, 1u) == total - 1) {  // last CTA: every CTA's stores are out
+            *done = 0;
+            __threadfence_system();
+            for (int r = 0; r < world; r++)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pd.flags[r] + rank), "l"(epoch) : "memory");
+        }
+    }
+}
+
+// one thread per peer: wait for its flag; a peer that never arrives trips the timeout (err = 1) instead of hanging
+__global__ void p2p_wait_kernel(const unsigned long long *flags, int world, unsigned long long epoch, long long timeout_cycles,
+                                int *err) {
+    if ((int)threadIdx.x >= world) return;
+    const long long t0 = clock64();
+    unsigned long long v = 0;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+        if (v >= epoch) return;
+    } while (clock64() - t0 < timeout_cycles);
+    *err = 1;
+}
+
+// out[b] = sum over the ranks (in rank order) of the |beta|^2 tails of an area
+__global__ void p2p_tail_kernel(const double *__restrict__ area, int world, long S, long tail_off, int B, double *__restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double acc = 0.0;
+    for (int r = 0; r < world; r++) acc += area[(size_t)r * S + tail_off + b];
+    out[b] = acc;
+}
+
 // ---- AMP iteration pieces (sparc_ldpc.py:203-220) -------------------------------------------------------------
 // s = beta + A^T z (partials summed in slice order); beta <- sqrt(n P_l) softmax_section(s sqrt(n P_l) / tau^2);
 // writes beta (fp64), its bf16x3 planes and sum(beta^2) per section.  One warp per section; inactive codewords
@@ -517,12 +578,14 @@ struct sb_dense {
     size_t part_elems;
     double *z, *tau2, *last_tau, *secsq;
     int *active, *n_active;
+    unsigned int *p2p_done;  // [0] CTA counter of p2p_push_kernel, [1] timeout flag of p2p_wait_kernel
     int secsq_L;
 };
 
 static void dense_free_ws(sb_dense *d) {
     cudaFree(d->zpl); cudaFree(d->bpl); cudaFree(d->part); cudaFree(d->z); cudaFree(d->tau2); cudaFree(d->last_tau);
-    cudaFree(d->secsq); cudaFree(d->active); cudaFree(d->n_active);
+    cudaFree(d->secsq); cudaFree(d->active); cudaFree(d->n_active); cudaFree(d->p2p_done);
+    d->p2p_done = nullptr;
     d->zpl = d->bpl = nullptr; d->part = d->z = d->tau2 = d->last_tau = d->secsq = nullptr; d->active = d->n_active = nullptr;
     d->capB = 0; d->part_elems = 0; d->secsq_L = 0;
 }
@@ -569,6 +632,7 @@ static int dense_reserve(sb_dense *d, int B, int L) {
     SB_CUDA(cudaMalloc(&d->secsq, sizeof(double) * (size_t)B * (L > 0 ? L : 1)));
     SB_CUDA(cudaMalloc(&d->active, sizeof(int) * B));
     SB_CUDA(cudaMalloc(&d->n_active, sizeof(int)));
+    SB_CUDA(cudaMalloc(&d->p2p_done, 2 * sizeof(unsigned int)));
     d->capB = B; d->part_elems = need_part; d->secsq_L = L > 0 ? L : 1;
     return SB_OK;
 }
@@ -656,6 +720,15 @@ extern "C" int sb_dense_create(const double *A_dev, int n, int LM, sb_dense **ou
     int rc = make_map(&d->mapA, d->A, n, LM, d->LMp, GM);
     if (rc == SB_OK) rc = make_map(&d->mapAt, d->At, LM, n, d->np, GM);
     if (rc != SB_OK) { cudaFree(d->A); cudaFree(d->At); delete d; return rc; }
+    {   // load the kernels of the peer-memory exchange now: a lazy module load at their first launch synchronises the
+        // context, which deadlocks if another rank of the SAME process (threads) is already spinning in p2p_wait_kernel
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, p2p_push_kernel);
+        cudaFuncGetAttributes(&fa, p2p_wait_kernel);
+        cudaFuncGetAttributes(&fa, p2p_tail_kernel);
+        cudaFuncGetAttributes(&fa, dense_sumsq_kernel);
+        cudaGetLastError();
+    }
     *out = d;
     return SB_OK;
 }
@@ -699,7 +772,8 @@ extern "C" int sb_dense_apply_batch(sb_dense *d, int transpose, const double *x,
 // ([B][n] + [B] doubles in xbuf) are summed over the ranks by the caller's `allreduce` once per iteration.
 static int dense_amp_impl(sb_dense *d, const double *y, const double *Pl, double P_total, const double *beta0, int L, int M,
                           int B, int T, double *beta, int *iters, int *n_exec, unsigned *flags, double *tau2_trace,
-                          sb_allreduce_fn allreduce, void *ctx, double *xbuf, cudaStream_t st) {
+                          sb_allreduce_fn allreduce, void *ctx, double *xbuf, cudaStream_t st, const sb_p2p *px = nullptr,
+                          unsigned long long *epoch_io = nullptr) {
     int rc = dense_reserve(d, B, L);
     if (rc != SB_OK) return rc;
     const int n = d->n, LM = d->LM;
@@ -708,7 +782,36 @@ static int dense_amp_impl(sb_dense *d, const double *y, const double *Pl, double
     if (tau2_trace) SB_CUDA(cudaMemsetAsync(tau2_trace, 0xFF, sizeof(double) * (size_t)B * T, st));  // NaN = not executed
     int slices = 0; long ss = 0;
     // after a GEMM of partial A beta: (sharded) fold the K slices into xbuf, append |beta|^2, sum over the ranks
+    // peer-memory exchange state (px != NULL): S doubles per slot, areas alternate with the epoch's parity
+    const long S = (long)B * n + B;
+    P2pDev pd;
+    unsigned long long epoch = epoch_io ? *epoch_io : 0;
+    const double *p2p_area = nullptr;
+    if (px) {
+        for (int r = 0; r < px->world; r++) { pd.slots[r] = px->slots[r]; pd.flags[r] = px->flags[r]; }
+        SB_CUDA(cudaMemsetAsync(d->p2p_done, 0, sizeof(unsigned int) + sizeof(int), st));
+    }
+    auto exchange_p2p = [&](bool with_sumsq) -> int {
+        epoch++;
+        const long area_off = (long)(epoch & 1ull) * px->world * S;
+        if (with_sumsq) {
+            dense_sumsq_kernel<<<B, 128, 0, st>>>(d->secsq, L, d->active, xbuf + (size_t)B * n);
+            SB_LAUNCHED();
+        }
+        dim3 gc((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024, B);
+        p2p_push_kernel<<<gc, 256, 0, st>>>(d->part, slices, ss, with_sumsq ? xbuf + (size_t)B * n : nullptr, n, B, pd,
+                                            px->rank, px->world, area_off, S, epoch, d->p2p_done);
+        SB_LAUNCHED();
+        p2p_wait_kernel<<<1, 32, 0, st>>>(px->flags[px->rank], px->world, epoch, (long long)px->timeout_ms * 2000000ll,
+                                          reinterpret_cast<int *>(d->p2p_done + 1));
+        SB_LAUNCHED();
+        p2p_area = px->slots[px->rank] + area_off;
+        p2p_tail_kernel<<<(B + 127) / 128, 128, 0, st>>>(p2p_area, px->world, S, (long)B * n, B, xbuf + (size_t)B * n);
+        SB_LAUNCHED();
+        return SB_OK;
+    };
     auto exchange = [&](bool with_sumsq) -> int {
+        if (px) return exchange_p2p(with_sumsq);
         if (!allreduce) return SB_OK;
         dim3 gc((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024, B);
         combine_kernel<<<gc, 256, 0, st>>>(d->part, slices, ss, nullptr, 1.0, n, xbuf);
@@ -723,8 +826,9 @@ static int dense_amp_impl(sb_dense *d, const double *y, const double *Pl, double
         if (r != 0) return fail(SB_ECUDA, "sb_dense_amp_batch_sharded: the allreduce callback failed%s (%ld)", "", (long)r);
         return SB_OK;
     };
+    const bool ext = allreduce || px;
     const double *xsrc = allreduce ? xbuf : d->part;
-    const double *sq_ext = allreduce ? xbuf + (size_t)B * n : nullptr;
+    const double *sq_ext = ext ? xbuf + (size_t)B * n : nullptr;
     if (beta0) {  // z = y - A beta0   (:197-198)
         if (beta0 != beta) SB_CUDA(cudaMemcpyAsync(beta, beta0, sizeof(double) * (size_t)B * LM, cudaMemcpyDeviceToDevice, st));
         dim3 g((d->LMp + 255) / 256 < 1024 ? (d->LMp + 255) / 256 : 1024, B);
@@ -737,7 +841,11 @@ static int dense_amp_impl(sb_dense *d, const double *y, const double *Pl, double
     } else {
         SB_CUDA(cudaMemsetAsync(beta, 0, sizeof(double) * (size_t)B * LM, st));
     }
-    dense_residual_kernel<<<B, 256, 0, st>>>(0, 0, beta0 ? xsrc : nullptr, allreduce ? 1 : slices, allreduce ? (long)B * n : ss, y,
+    // partial sums the residual kernel adds up: K slices (one GPU), the all-reduced buffer, or the world's slots
+    auto res_src = [&]() { return px ? p2p_area : xsrc; };
+    auto res_cnt = [&]() { return px ? px->world : (allreduce ? 1 : slices); };
+    auto res_str = [&]() { return px ? S : (allreduce ? (long)B * n : ss); };
+    dense_residual_kernel<<<B, 256, 0, st>>>(0, 0, beta0 ? res_src() : nullptr, res_cnt(), res_str(), y,
                                              d->secsq, Pl, L, n, d->np, B, d->z, d->zpl, d->tau2, d->last_tau, d->active, iters,
                                              n_exec, flags, tau2_trace, T, d->n_active, sq_ext, P_total);
     SB_LAUNCHED();
@@ -752,7 +860,7 @@ static int dense_amp_impl(sb_dense *d, const double *y, const double *Pl, double
         if (rc != SB_OK) return rc;
         rc = exchange(true);
         if (rc != SB_OK) return rc;
-        dense_residual_kernel<<<B, 256, 0, st>>>(1, t, xsrc, allreduce ? 1 : slices, allreduce ? (long)B * n : ss, y, d->secsq, Pl,
+        dense_residual_kernel<<<B, 256, 0, st>>>(1, t, res_src(), res_cnt(), res_str(), y, d->secsq, Pl,
                                                  L, n, d->np, B, d->z, d->zpl, d->tau2, d->last_tau, d->active, iters, n_exec,
                                                  flags, tau2_trace, T, d->n_active, sq_ext, P_total);
         SB_LAUNCHED();
@@ -762,6 +870,13 @@ static int dense_amp_impl(sb_dense *d, const double *y, const double *Pl, double
             SB_CUDA(cudaStreamSynchronize(st));
             if (na <= 0) break;
         }
+    }
+    if (px) {
+        if (epoch_io) *epoch_io = epoch;
+        int perr = 0;
+        SB_CUDA(cudaMemcpyAsync(&perr, d->p2p_done + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        if (perr) return fail(SB_ECUDA, "sb_dense_amp_batch_p2p: a peer did not arrive within the timeout%s", "");
     }
     return SB_OK;
 }
@@ -775,6 +890,36 @@ extern "C" int sb_dense_amp_batch(sb_dense *d, const double *y, const double *Pl
     if (B == 0) return SB_OK;
     return dense_amp_impl(d, y, Pl, 0.0, beta0, L, M, B, T, beta, iters, n_exec, flags, tau2_trace, nullptr, nullptr, nullptr,
                           (cudaStream_t)stream);
+}
+
+// lets kernels of the current device store into / load from `peer_device`'s memory (IPC-mapped receive areas)
+extern "C" int sb_enable_peer_access(int peer_device) {
+    int cur = -1;
+    SB_CUDA(cudaGetDevice(&cur));
+    if (cur == peer_device) return SB_OK;
+    int can = 0;
+    SB_CUDA(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+    if (!can) return fail(SB_ECUDA, "sb_enable_peer_access: no peer access to device%s %ld", "", (long)peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return SB_OK; }
+    SB_CUDA(e);
+    return SB_OK;
+}
+
+extern "C" int sb_dense_amp_batch_p2p(sb_dense *d, const double *y, const double *Pl_local, double P_total,
+                                      const double *beta0_local, int L_local, int M, int B, int T, double *beta_local,
+                                      int *iters, int *n_exec, unsigned *flags, double *tau2_trace, double *xbuf,
+                                      const sb_p2p *px, unsigned long long *epoch_io, void *stream) {
+    if (!d || !y || !Pl_local || !beta_local || !iters || !n_exec || !flags || !xbuf || !px || !epoch_io || B < 0 || T < 0 ||
+        L_local <= 0 || M <= 0 || px->world < 1 || px->world > SB_P2P_MAX || px->rank < 0 || px->rank >= px->world)
+        return fail(SB_EINVAL, "sb_dense_amp_batch_p2p: bad argument%s", "");
+    for (int r = 0; r < px->world; r++)
+        if (!px->slots[r] || !px->flags[r]) return fail(SB_EINVAL, "sb_dense_amp_batch_p2p: peer %s%ld not mapped", "", (long)r);
+    if ((long)L_local * M != d->LM)
+        return fail(SB_EINVAL, "sb_dense_amp_batch_p2p: L_local*M does not match the matrix%s (%ld)", "", (long)L_local * M);
+    if (B == 0) return SB_OK;
+    return dense_amp_impl(d, y, Pl_local, P_total, beta0_local, L_local, M, B, T, beta_local, iters, n_exec, flags, tau2_trace,
+                          nullptr, nullptr, xbuf, (cudaStream_t)stream, px, epoch_io);
 }
 
 extern "C" int sb_dense_amp_batch_sharded(sb_dense *d, const double *y, const double *Pl_local, double P_total,

@@ -275,6 +275,102 @@ class DenseOperator:
         return AmpResult(beta, iters, n_exec, flags, tau2)
 
 
+    def amp_p2p(self, y, Pl_local, P_total, T, peers, beta0=None, trace=False, before_launch=None):
+        """Column-sharded AMP with the per-iteration exchange over NVLink peer memory (sb_dense_amp_batch_p2p): no
+        collective library in the loop.  `peers` is this rank's PeerExchange (receive areas and flag words of all
+        ranks, mapped here).  Same arguments and result as amp_sharded.  `before_launch()` (optional) runs after
+        this call's device allocations and right before the kernels are queued: ranks that are THREADS of one
+        process rendezvous there, because a cudaMalloc of one thread can wait for the whole device, i.e. for a peer
+        thread's kernel that is already spinning on this thread's flag (separate processes need nothing)."""
+        import ctypes as ct
+        _chk(y, F64, "y")
+        _chk(Pl_local, F64, "Pl_local")
+        _chk(beta0, F64, "beta0")
+        B, n = y.shape
+        if n != self.n or Pl_local.numel() != self.L:
+            raise ValueError("y must be [B, n] and Pl_local [L_local]")
+        if B * n + B > peers.slot_doubles:
+            raise ValueError("the peer areas were allocated for a smaller batch")
+        dev = y.device
+        xbuf = torch.empty(B * n + B, dtype=F64, device=dev)
+        beta = torch.empty((B, self.L * self.M), dtype=F64, device=dev)
+        iters = torch.empty(B, dtype=I32, device=dev)
+        n_exec = torch.empty(B, dtype=I32, device=dev)
+        flags = torch.empty(B, dtype=I32, device=dev)
+        tau2 = torch.empty((B, max(T, 1)), dtype=F64, device=dev) if trace else None
+        if before_launch is not None:
+            before_launch()
+        rc = _lib.lib().sb_dense_amp_batch_p2p(self._h, _p(y), _p(Pl_local), float(P_total), _p(beta0), self.L, self.M, B,
+                                               int(T), _p(beta), _p(iters), _p(n_exec), _p(flags), _p(tau2), _p(xbuf),
+                                               ct.addressof(peers.cstruct), ct.addressof(peers.epoch), _stream())
+        check(rc, "sb_dense_amp_batch_p2p")
+        return AmpResult(beta, iters, n_exec, flags, tau2)
+
+
+class PeerExchange:
+    """Receive areas ([2][world][B n + B] doubles) and flag words ([world] uint64) of every rank of a column-sharded
+    dense operator, mapped into this process (include/sparc_b200.h sb_p2p)."""
+
+    class _C(__import__("ctypes").Structure):
+        import ctypes as _ct
+        _fields_ = [("rank", _ct.c_int), ("world", _ct.c_int), ("timeout_ms", _ct.c_int),
+                    ("slots", _ct.c_void_p * 8), ("flags", _ct.c_void_p * 8)]
+
+    def __init__(self, rank, world, slot_doubles, areas, flagws, timeout_ms=20000):
+        import ctypes as ct
+        if world > 8:
+            raise ValueError("at most 8 ranks (one NVSwitch domain)")
+        self.rank, self.world, self.slot_doubles = rank, world, slot_doubles
+        self._keep = (areas, flagws)          # the mapped tensors must outlive the exchange
+        self.cstruct = PeerExchange._C()
+        self.cstruct.rank, self.cstruct.world, self.cstruct.timeout_ms = rank, world, int(timeout_ms)
+        for r in range(world):
+            self.cstruct.slots[r] = areas[r].data_ptr()
+            self.cstruct.flags[r] = flagws[r].data_ptr()
+        self.epoch = ct.c_ulonglong(0)
+
+    @staticmethod
+    def _alloc(world, B, n, dev):
+        S = B * n + B
+        return S, torch.zeros(2 * world * S, dtype=F64, device=dev), torch.zeros(world, dtype=torch.int64, device=dev)
+
+    @staticmethod
+    def in_process(world, B, n, dev=None):
+        """All ranks live in this process (threads, one stream each, same or different GPUs of the process)."""
+        dev = dev or _dev()
+        allocs = [PeerExchange._alloc(world, B, n, dev) for _ in range(world)]
+        areas, flagws = [a[1] for a in allocs], [a[2] for a in allocs]
+        torch.cuda.synchronize()
+        return [PeerExchange(r, world, allocs[0][0], areas, flagws) for r in range(world)]
+
+    @staticmethod
+    def from_process_group(B, n, group=None, timeout_ms=20000):
+        """One process per GPU (torchrun): every rank allocates its area on its own GPU, the CUDA IPC handles travel
+        through torch.distributed, every rank maps its peers' memory and enables peer access."""
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        dev = _dev()
+        S, area, flagw = PeerExchange._alloc(world, B, n, dev)
+        torch.cuda.synchronize()
+        mine = (torch.cuda.current_device(), reduce_tensor(area), reduce_tensor(flagw))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine, group=group)
+        areas, flagws = [], []
+        for r, (pdev, (fa, aa), (ff, af)) in enumerate(everyone):
+            if r == rank:
+                areas.append(area)
+                flagws.append(flagw)
+                continue
+            check(_lib.lib().sb_enable_peer_access(int(pdev)), "sb_enable_peer_access")
+            areas.append(fa(*aa))
+            flagws.append(ff(*af))
+        dist.barrier(group=group)             # every area is zeroed and mapped before anyone pushes
+        px = PeerExchange(rank, world, S, areas, flagws, timeout_ms)
+        px._own = (area, flagw)
+        return px
+
+
 _OP_CACHE = {}
 
 

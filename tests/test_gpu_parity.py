@@ -307,6 +307,26 @@ def test_gaussian_column_sharded_matches_unsharded(Eng, oracle):
         assert e_ref < NORTH_STAR_RTOL and e_full < NORTH_STAR_RTOL
 
 
+def test_gaussian_column_sharded_peer_memory_exchange():
+    """The column-sharded decode with the exchange over peer memory (sb_dense_amp_batch_p2p): every shard pushes its
+    partial A beta into a slot of every peer's receive area, publishes an epoch flag, waits for the peers' flags and
+    adds the slots in rank order -- no collective library, no host in the loop.  Two ranks as two PROCESSES on this
+    one GPU (tools/gaussian_sharded.py --same-gpu: the receive areas are mapped with CUDA IPC exactly as between
+    GPUs; the two contexts are time-sliced, so the spinning wait kernels still make progress).  --check requires the
+    same iteration counts as the all-reduce path, beta equal to 1e-9 and two identical consecutive runs."""
+    import os
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [_sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "gaussian_sharded.py"), "--same-gpu", "--check", "--p2p",
+           "--L", "128", "--M", "4", "--rows", "256", "--B", "8", "--T", "24", "--reps", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+    print(r.stdout[-1500:])
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "check: peer-memory exchange vs all-reduce" in r.stdout and "-> OK" in r.stdout
+
+
 @pytest.mark.parametrize("shape", [(256, 512, 100), (130, 200, 7), (384, 1000, 129), (4608, 2048, 40), (640, 40000, 130)])
 def test_dense_gemm_bf16x3_against_fp64(Eng, shape):
     """The tcgen05 / TMA GEMM of the Gaussian mode alone: A x and A^T x for ragged shapes (rows not a multiple of

@@ -1,7 +1,13 @@
-"""Column-sharded Gaussian-mode AMP over NCCL: rank r holds the columns of sections [r L/W, (r+1) L/W) of a dense
-design matrix; one all-reduce of [B*(n+1)] doubles per AMP iteration (sb_dense_amp_batch_sharded).
+"""Column-sharded Gaussian-mode AMP: rank r holds the columns of sections [r L/W, (r+1) L/W) of a dense design
+matrix; per AMP iteration the partial A beta ([B*(n+1)] doubles) is exchanged either with one NCCL all-reduce
+(sb_dense_amp_batch_sharded) or, with --p2p, by pushing it into the peers' memory over NVLink
+(sb_dense_amp_batch_p2p: receive areas mapped with CUDA IPC, epoch flags, no collective library in the loop).
 
-  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/gaussian_sharded.py [--L 2048 --M 32 --n 10240 --B 128]
+  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/gaussian_sharded.py [--p2p] [--L 2048 --M 32 --rows 10240 --B 128]
+
+--same-gpu puts every rank on GPU 0 (gloo rendezvous; the contexts are time-sliced, so spinning kernels still make
+progress): the single-GPU test of the IPC path.  --check compares both exchanges with each other (bit for bit) and
+exits non-zero on a mismatch.
 
 Every rank generates the same seeded matrix column block by block, so no rank ever holds the whole A."""
 import argparse
@@ -18,18 +24,40 @@ from sparc_ldpc_b200 import engine as E  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--L", type=int, default=2048)
 ap.add_argument("--M", type=int, default=32)
-ap.add_argument("--n", type=int, default=10240)
+ap.add_argument("--rows", dest="n", type=int, default=10240, help="n, the codeword length (named --rows: torchrun mis-parses --n)")
 ap.add_argument("--B", type=int, default=128)
 ap.add_argument("--P", type=float, default=4.0)
 ap.add_argument("--sigma", type=float, default=0.7)
 ap.add_argument("--T", type=int, default=32)
+ap.add_argument("--p2p", action="store_true", help="exchange over peer memory instead of NCCL")
+ap.add_argument("--same-gpu", action="store_true", help="all ranks on GPU 0, gloo for the host-side rendezvous")
+ap.add_argument("--check", action="store_true", help="run both exchanges and require identical results")
+ap.add_argument("--reps", type=int, default=3)
 args = ap.parse_args()
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+if args.same_gpu:
+    local = 0
 torch.cuda.set_device(local)
 if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.same_gpu:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+
+def allreduce_any(t, op=None):
+    """sum / max over the ranks with whatever backend is up (gloo has no CUDA tensors)"""
+    op = op or dist.ReduceOp.SUM
+    if args.same_gpu:
+        c = t.cpu()
+        dist.all_reduce(c, op=op)
+        t.copy_(c)
+    else:
+        dist.all_reduce(t, op=op)
+
+
 L, M, n, B = args.L, args.M, args.n, args.B
 assert L % world == 0
 Ll = L // world
@@ -51,17 +79,36 @@ mine = idx[:, rank * Ll:(rank + 1) * Ll]
 b0.scatter_(1, (torch.arange(Ll, device="cuda") * M)[None, :] + mine, float(np.sqrt(n * args.P / L)))
 x = b0 @ A_local.t()
 if world > 1:
-    dist.all_reduce(x)
+    allreduce_any(x)
 y = x + noise
 op = E.DenseOperator(A_local, Ll, M)
-for rep in range(3):
+peers = E.PeerExchange.from_process_group(B, n) if (world > 1 and (args.p2p or args.check)) else None
+Pl_loc = Pl[rank * Ll:(rank + 1) * Ll].contiguous()
+if args.check and world > 1:
+    a = op.amp_sharded(y, Pl_loc, args.P, args.T, allreduce=allreduce_any)
+    b = op.amp_p2p(y, Pl_loc, args.P, args.T, peers)
+    c = op.amp_p2p(y, Pl_loc, args.P, args.T, peers)
+    torch.cuda.synchronize()
+    same = torch.equal(b.beta, c.beta) and torch.equal(a.iters, b.iters) and torch.equal(a.n_exec, b.n_exec)
+    rel = float((a.beta - b.beta).abs().max() / a.beta.abs().max())
+    # the all-reduce adds the ranks' partial sums in the library's order, the peer exchange in rank order
+    ok = torch.tensor([1.0 if (same and rel < 1e-9) else 0.0], dtype=torch.float64, device="cuda")
+    allreduce_any(ok, dist.ReduceOp.MIN)
+    if rank == 0:
+        print("check: peer-memory exchange vs all-reduce: max rel beta difference %.2e, iterations %s, repeatable %s -> %s"
+              % (rel, b.iters[:4].tolist(), same, "OK" if float(ok) == 1.0 else "MISMATCH"))
+    if float(ok) != 1.0:
+        sys.exit(1)
+for rep in range(args.reps):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    if world > 1:
-        res = op.amp_sharded(y, Pl[rank * Ll:(rank + 1) * Ll].contiguous(), args.P, args.T)
+    if world > 1 and args.p2p:
+        res = op.amp_p2p(y, Pl_loc, args.P, args.T, peers)
+    elif world > 1:
+        res = op.amp_sharded(y, Pl_loc, args.P, args.T, allreduce=allreduce_any if args.same_gpu else None)
     else:
         res = op.amp(y, Pl, args.T)
     e1.record()
@@ -70,12 +117,13 @@ for rep in range(3):
     errs = (dec != mine).sum().to(torch.float64)
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(errs)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        allreduce_any(errs)
+        allreduce_any(ms, dist.ReduceOp.MAX)
     if rank == 0:
         its = int(res.n_exec.max())
         print("world %d rep %d: %.2f ms for %d codewords x %d iterations (L=%d M=%d n=%d, %d sections per rank), "
-              "section error rate %.4f, all-reduce of %.2f MB per iteration"
-              % (world, rep, float(ms), B, its, L, M, n, Ll, float(errs) / (B * L), (B * n + B) * 8 / 1e6))
+              "section error rate %.4f, %s of %.2f MB per iteration"
+              % (world, rep, float(ms), B, its, L, M, n, Ll, float(errs) / (B * L),
+                 "peer-memory push" if args.p2p else "all-reduce", (B * n + B) * 8 / 1e6))
 if world > 1:
     dist.destroy_process_group()
