@@ -201,6 +201,12 @@ typedef struct {
     unsigned long long *flags[SB_P2P_MAX];
 } sb_p2p;
 int sb_enable_peer_access(int peer_device); /* cudaDeviceEnablePeerAccess from the current device */
+/* receive areas shared between processes: cudaMalloc + cudaIpcGetMemHandle on the owner (zero-initialised),
+ * cudaIpcOpenMemHandle(cudaIpcMemLazyEnablePeerAccess) on every peer WITH ITS OWN DEVICE CURRENT */
+int sb_p2p_alloc(long bytes, void **dev_ptr, unsigned char *handle64);
+int sb_p2p_open(const unsigned char *handle64, void **dev_ptr);
+int sb_p2p_close(void *dev_ptr);
+int sb_p2p_free(void *dev_ptr);
 int sb_dense_amp_batch_p2p(sb_dense *d, const double *y, const double *Pl_local, double P_total,
                            const double *beta0_local, int L_local, int M, int B, int T, double *beta_local, int *iters,
                            int *n_exec, unsigned *flags, double *tau2_trace, double *xbuf, const sb_p2p *peers,

@@ -51,6 +51,10 @@ SIGNATURES = {
     "sb_dense_amp_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_dense_amp_batch_sharded": (_i, [_vp, _vp, _vp, _d, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_enable_peer_access": (_i, [_i]),
+    "sb_p2p_alloc": (_i, [_l, ct.POINTER(_vp), _vp]),
+    "sb_p2p_open": (_i, [_vp, ct.POINTER(_vp)]),
+    "sb_p2p_close": (_i, [_vp]),
+    "sb_p2p_free": (_i, [_vp]),
     "sb_dense_amp_batch_p2p": (_i, [_vp, _vp, _vp, _d, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_argmax_batch": (_i, [_vp, _l, _i, _i, _i, _vp, _l, _vp]),
     "sb_llr2idx_batch": (_i, [_vp, _l, _i, _i, _i, _vp, _l, _vp]),

@@ -906,6 +906,38 @@ extern "C" int sb_enable_peer_access(int peer_device) {
     return SB_OK;
 }
 
+// Receive areas of the peer-memory exchange: plain cudaMalloc blocks (zeroed) exported / imported with CUDA IPC.  The
+// import runs with the ACCESSING device current and cudaIpcMemLazyEnablePeerAccess, which is what maps the peer's
+// memory into this device's address space (a handle opened under the owner's device is not reachable from here).
+extern "C" int sb_p2p_alloc(long bytes, void **dev_ptr, unsigned char *handle64) {
+    if (!dev_ptr || !handle64 || bytes <= 0) return fail(SB_EINVAL, "sb_p2p_alloc: bad argument%s", "");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    void *p = nullptr;
+    SB_CUDA(cudaMalloc(&p, (size_t)bytes));
+    SB_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); SB_CUDA(e); }
+    memcpy(handle64, &h, 64);
+    *dev_ptr = p;
+    return SB_OK;
+}
+extern "C" int sb_p2p_open(const unsigned char *handle64, void **dev_ptr) {
+    if (!dev_ptr || !handle64) return fail(SB_EINVAL, "sb_p2p_open: bad argument%s", "");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    SB_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SB_OK;
+}
+extern "C" int sb_p2p_close(void *dev_ptr) {
+    if (dev_ptr) SB_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return SB_OK;
+}
+extern "C" int sb_p2p_free(void *dev_ptr) {
+    if (dev_ptr) SB_CUDA(cudaFree(dev_ptr));
+    return SB_OK;
+}
+
 extern "C" int sb_dense_amp_batch_p2p(sb_dense *d, const double *y, const double *Pl_local, double P_total,
                                       const double *beta0_local, int L_local, int M, int B, int T, double *beta_local,
                                       int *iters, int *n_exec, unsigned *flags, double *tau2_trace, double *xbuf,

@@ -345,30 +345,57 @@ class PeerExchange:
 
     @staticmethod
     def from_process_group(B, n, group=None, timeout_ms=20000):
-        """One process per GPU (torchrun): every rank allocates its area on its own GPU, the CUDA IPC handles travel
-        through torch.distributed, every rank maps its peers' memory and enables peer access."""
+        """One process per GPU (torchrun): every rank allocates its area (sb_p2p_alloc: cudaMalloc, zeroed) on its own
+        GPU, the 64-byte CUDA IPC handles travel through torch.distributed, and every rank opens its peers' handles
+        with its own device current (sb_p2p_open), which maps the peers' memory for this GPU over NVLink."""
+        import ctypes as ct
         import torch.distributed as dist
-        from torch.multiprocessing.reductions import reduce_tensor
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-        dev = _dev()
-        S, area, flagw = PeerExchange._alloc(world, B, n, dev)
-        torch.cuda.synchronize()
-        mine = (torch.cuda.current_device(), reduce_tensor(area), reduce_tensor(flagw))
+        _dev()
+        L = _lib.lib()
+        S = B * n + B
+        area_bytes = 2 * world * S * 8
+        base, hbuf = ct.c_void_p(), (ct.c_ubyte * 64)()
+        check(L.sb_p2p_alloc(area_bytes + world * 8, ct.byref(base), ct.addressof(hbuf)), "sb_p2p_alloc")
         everyone = [None] * world
-        dist.all_gather_object(everyone, mine, group=group)
-        areas, flagws = [], []
-        for r, (pdev, (fa, aa), (ff, af)) in enumerate(everyone):
+        dist.all_gather_object(everyone, (torch.cuda.current_device(), bytes(hbuf)), group=group)
+        bases = []
+        for r, (pdev, handle) in enumerate(everyone):
             if r == rank:
-                areas.append(area)
-                flagws.append(flagw)
+                bases.append(base.value)
                 continue
-            check(_lib.lib().sb_enable_peer_access(int(pdev)), "sb_enable_peer_access")
-            areas.append(fa(*aa))
-            flagws.append(ff(*af))
+            if pdev != torch.cuda.current_device():
+                check(L.sb_enable_peer_access(int(pdev)), "sb_enable_peer_access")
+            p, hb = ct.c_void_p(), (ct.c_ubyte * 64).from_buffer_copy(handle)
+            check(L.sb_p2p_open(ct.addressof(hb), ct.byref(p)), "sb_p2p_open")
+            bases.append(p.value)
         dist.barrier(group=group)             # every area is zeroed and mapped before anyone pushes
-        px = PeerExchange(rank, world, S, areas, flagws, timeout_ms)
-        px._own = (area, flagw)
+
+        class _Ptr:                            # what PeerExchange needs from a tensor
+            def __init__(self, addr):
+                self.addr = addr
+
+            def data_ptr(self):
+                return self.addr
+
+        px = PeerExchange(rank, world, S, [_Ptr(b) for b in bases], [_Ptr(b + area_bytes) for b in bases], timeout_ms)
+        px._bases, px._group = bases, group
         return px
+
+    def close(self):
+        """Unmap the peers' areas and free the local one (collective: every rank calls it)."""
+        bases = getattr(self, "_bases", None)
+        if not bases:
+            return
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier(group=self._group)       # nobody still pushes into memory that is about to go away
+        for r, b in enumerate(bases):
+            if r != self.rank:
+                _lib.lib().sb_p2p_close(b)
+        dist.barrier(group=self._group)
+        _lib.lib().sb_p2p_free(bases[self.rank])
+        self._bases = None
 
 
 _OP_CACHE = {}

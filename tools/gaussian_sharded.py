@@ -125,5 +125,7 @@ for rep in range(args.reps):
               "section error rate %.4f, %s of %.2f MB per iteration"
               % (world, rep, float(ms), B, its, L, M, n, Ll, float(errs) / (B * L),
                  "peer-memory push" if args.p2p else "all-reduce", (B * n + B) * 8 / 1e6))
+if peers is not None:
+    peers.close()
 if world > 1:
     dist.destroy_process_group()
