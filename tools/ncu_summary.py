@@ -43,7 +43,13 @@ def main():
         f.write("metric,unit," + ",".join(c[0] for c in cols) + "\n")
         for m in metrics:
             unit = next((c[2][m][0] for c in cols if m in c[2]), "")
-            f.write(m + "," + unit + "," + ",".join(c[2].get(m, ("", ""))[1].replace(",", "") for c in cols) + "\n")
+            # ncu picks a unit per report: a cell whose unit differs from the column header's carries its own
+            cells = []
+            for c in cols:
+                u, v = c[2].get(m, ("", ""))
+                v = v.replace(",", "")
+                cells.append(v if (u == unit or not v) else v + " " + u)
+            f.write(m + "," + unit + "," + ",".join(cells) + "\n")
 
 
 if __name__ == "__main__":
