@@ -354,7 +354,7 @@ def gpu_arm(args):
                          "kernel_busy_fraction_of_timed_region": amp_ms / ms,
                          "avg_launch_ms": amp_ms / max(n_amp_launch, 1),
                          "algorithmic_bytes_per_launch": alg_bytes / max(n_amp_launch, 1),
-                         "co_limiter": "not HBM: the L1 data pipe (2 L n random shared-memory reads + 25 KB of L2-resident table words per section) is 66% busy, issue 45%, fp64 21%; stalls: long-scoreboard 18% (table loads), MIO queue 17%, barrier 7% (profiles/r01_amp_kernel_ncu_full.csv v10, r01_amp_phase_clocks.txt)"},
+                         "co_limiter": "not HBM: the L1 data pipe (2 L n random shared-memory reads + 25 KB of L2-resident table words per section) is 68% busy, issue 47%, fp64 22%; stalls: long-scoreboard (table loads), MIO queue, barrier (profiles/r01_amp_kernel_ncu_full.csv v11, r01_amp_phase_clocks.txt)"},
             "clocks": clocks.summary(),
         }
         if world == 1 and not args.no_cpu:
