@@ -366,6 +366,7 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
 #pragma unroll
             // beta streams through once per iteration: L1::no_allocate loads and streaming stores keep it out of
             // the L1 lines that the table loads in flight need (2.94 -> 2.81 us per codeword-iteration)
+            // (the table loads themselves want the default policy: L1::no_allocate / evict_first on them cost 4 %)
             for (int e = 0; e < EPT; e++) {
                 bv[e] = 0.0;
                 if (!first_zero) asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(bv[e]) : "l"(bsrc + e * TEAM + q));
