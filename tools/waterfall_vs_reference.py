@@ -22,8 +22,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=2368, help="codewords per Eb/N0 point (all ranks together)")
 ap.add_argument("--flow", default="soft", choices=["soft", "hard", "originalHard"])
 ap.add_argument("--amp-mode", default="fast")
+ap.add_argument("--bp-mode", default="fast", help="engine.BP_MODE: strict | fast (the bench runs fast)")
 ap.add_argument("--out", default="")
 args = ap.parse_args()
+E.BP_MODE = args.bp_mode
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
@@ -55,7 +57,7 @@ for i, r in enumerate(ref["rows"]):
                  r["BER_amp_1"], r["BER_ldpc"], r["BER_amp_2"], r["BER_ldpc_2"], r["BER_plain"]), flush=True)
 if rank == 0:
     out = {"flow": args.flow, "reference_csv": ref["source"], "codewords_per_point": args.n, "n_gpus": world,
-           "amp_mode": args.amp_mode, "wall_s": time.time() - t0, "rows": rows}
+           "amp_mode": args.amp_mode, "bp_mode": args.bp_mode, "wall_s": time.time() - t0, "rows": rows}
     if args.out:
         json.dump(out, open(args.out, "w"), indent=1)
     print("wall %.1f s for %d points x %d codewords (coded + plain) on %d GPU(s)" % (out["wall_s"], len(rows), args.n, world))
