@@ -126,7 +126,8 @@ int sb_onehot_apply_batch(const sb_operator *op, const int *idx, const double *P
                            above the quantisation floor), so `iters` is smaller than in STRICT mode.                */
 int sb_amp_batch(const sb_operator *op, const double *y, const double *Pl, const double *beta0, const int *sections,
                  const int *nsec, int B, int T, int mode, double *beta, int *iters, int *n_exec, unsigned *flags,
-                 double *tau2_trace, double *scratch /* [B][n] work space, required in FAST mode */, void *stream);
+                 double *tau2_trace, double *scratch /* [2][B][n] work space, required in FAST mode: z and, for n > 8191,
+                                                        the A beta accumulator */, void *stream);
 
 /* ------------------------------------------------------------------ (2c) section <-> bit handoff
  * p = sp2bp(beta / sqrt(n*Pl)) (sparc_ldpc.py:257-281, :657); llr = nan_to_num(log(1-p) - log(p)) (:667-669).

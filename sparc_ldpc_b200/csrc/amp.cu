@@ -357,7 +357,7 @@ extern "C" int sb_amp_batch(const sb_operator *op, const double *y, const double
         return fail(SB_EINVAL, "sb_amp_batch: null argument%s", "");
     if (mode != SB_AMP_STRICT && mode != SB_AMP_FAST) return fail(SB_EINVAL, "sb_amp_batch: unknown mode%s %ld", "", mode);
     if ((sections == nullptr) != (nsec == nullptr)) return fail(SB_EINVAL, "sb_amp_batch: sections and nsec go together%s", "");
-    if (mode == SB_AMP_FAST && op->qok && !scratch) return fail(SB_EINVAL, "sb_amp_batch: FAST mode needs a [B][n] scratch%s", "");
+    if (mode == SB_AMP_FAST && op->qok && !scratch) return fail(SB_EINVAL, "sb_amp_batch: FAST mode needs a [2][B][n] scratch%s", "");
     if (B == 0) return SB_OK;
     AmpArgs a = base_args(op, sections, nsec);
     a.zscratch = scratch;

@@ -710,14 +710,17 @@ struct Smem {
         const int regions = (W + TeamCfg<LOGM>::SPR - 1) / TeamCfg<LOGM>::SPR;
         return (size_t)regions * ((QUANT ? 2 : 4) << TeamCfg<LOGM>::SBQ);
     }
-    __host__ __device__ static size_t bytes(int n, int W) {
+    // accg: the A beta accumulator lives in the codeword's global scratch row instead (shapes with w/M = 32, i.e.
+    // n > 8191: with it in shared memory the CTA needs 203 KB, the carve-out becomes 228 KB and no L1 is left for the
+    // table loads in flight -- see the carve-out experiments in DESIGN.md section 6)
+    __host__ __device__ static size_t bytes(int n, int W, int accg = 0) {
         size_t b = QUANT ? sizeof(int) * (size_t)pad4(2 * n + 32) : sizeof(double) * (size_t)pad2(n + 1);
-        b += sizeof(double) * (size_t)pad2(n);  // acc
+        if (!accg) b += sizeof(double) * (size_t)pad2(n);  // acc
         b += f_bytes(W);
         b += sizeof(double) * 40 + sizeof(int) * (size_t)(W + 2);
         return b;
     }
-    __device__ Smem(unsigned char *raw, int n, int W) {
+    __device__ Smem(unsigned char *raw, int n, int W, int accg = 0) {
         if (QUANT) {
             zq = reinterpret_cast<int *>(raw);
             zf = nullptr;
@@ -727,7 +730,7 @@ struct Smem {
             zf = reinterpret_cast<double *>(raw);
             acc = zf + pad2(n + 1);
         }
-        F = reinterpret_cast<char *>(acc + pad2(n));
+        F = reinterpret_cast<char *>(acc + (accg ? 0 : pad2(n)));
         red = reinterpret_cast<double *>(F + f_bytes(W));
         sec = reinterpret_cast<int *>(red + 40);
     }
@@ -742,12 +745,14 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
     constexpr int M = TeamCfg<LOGM>::M;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, b = blockIdx.x;
-    Smem<LOGM, QUANT> sm(smem_raw, n, W);
+    constexpr int ACCG = (QUANT && NBT == 2) ? 1 : 0;
+    Smem<LOGM, QUANT> sm(smem_raw, n, W, ACCG);
     double *zf = QUANT ? a.zscratch + (size_t)b * n : sm.zf;  // every thread only touches its own k = tid + j*NT
-    double *acc_s = sm.acc, *red = sm.red;
+    // (likewise the accumulator: thread tid owns rows tid + j*NT in the gather, the reset and the z update)
+    double *acc_s = ACCG ? a.zscratch + ((size_t)gridDim.x + b) * n : sm.acc, *red = sm.red;
     // sqrt(n P_l) of the i-th active section, staged once behind the other arrays (a per-section global load and
     // sqrt at the top of every section stalled the warp: 2.4 % of the stall samples)
-    double *rtp = reinterpret_cast<double *>(smem_raw + ((Smem<LOGM, QUANT>::bytes(n, W) + 7) & ~(size_t)7));
+    double *rtp = reinterpret_cast<double *>(smem_raw + ((Smem<LOGM, QUANT>::bytes(n, W, ACCG) + 7) & ~(size_t)7));
     if (QUANT) {
         if (threadIdx.x < 32) sm.zq[n + threadIdx.x] = 0;  // one zero word per bank
     } else if (threadIdx.x == 0) {
@@ -924,7 +929,7 @@ __global__ void __launch_bounds__(512, 1) Az_kernel(AmpArgs a, int W, const doub
 // 256-thread CTAs per SM, whose gather (shared-memory pipe) and transform (fp64 / issue) phases then overlap.
 // Never more teams than sections, never more shared memory than 227 KB.
 template <int LOGM, bool QUANT>
-static int pick_threads(int n, int L, int pw, size_t *smem_out, int *W_out) {
+static int pick_threads(int n, int L, int pw, size_t *smem_out, int *W_out, int accg = 0) {
     constexpr int TEAM = TeamCfg<LOGM>::TEAM;
     int nt = 512;
     // FAST: two 256-thread CTAs per SM when the operator's gather table was built for 8-section chunks (or, for
@@ -938,9 +943,9 @@ static int pick_threads(int n, int L, int pw, size_t *smem_out, int *W_out) {
     if (nt < 32) nt = 32;
     if (nt < TEAM) nt = TEAM;
     while (nt > 64 && (nt / 2) / TEAM >= L) nt /= 2;
-    while (nt > 32 && nt > TEAM && Smem<LOGM, QUANT>::bytes(n, nt / TEAM) + 8 * (size_t)L + 8 > 227 * 1024) nt /= 2;
+    while (nt > 32 && nt > TEAM && Smem<LOGM, QUANT>::bytes(n, nt / TEAM, accg) + 8 * (size_t)L + 8 > 227 * 1024) nt /= 2;
     *W_out = nt / TEAM;
-    *smem_out = ((Smem<LOGM, QUANT>::bytes(n, *W_out) + 7) & ~(size_t)7) + sizeof(double) * (size_t)L;  // + rtp[L]
+    *smem_out = ((Smem<LOGM, QUANT>::bytes(n, *W_out, accg) + 7) & ~(size_t)7) + sizeof(double) * (size_t)L;  // + rtp[L]
     return nt;
 }
 
@@ -950,7 +955,9 @@ int launch_amp(const sb_operator *op, AmpArgs a, int B, int which, const double 
     size_t smem = 0;
     int W = 0;
     const bool quant = (which == 3) && op->qok;
-    const int nt = quant ? pick_threads<LOGM, true>(op->n, op->L, op->PW, &smem, &W)
+    const int nbt0 = (op->NB == 1) ? 1 : ((op->NB == 2 && LOGM == 9) ? 2 : 0);
+    const int accg = (quant && nbt0 == 2 && !op->qpre) ? 1 : 0;  // = ACCG of the kernel dispatched below
+    const int nt = quant ? pick_threads<LOGM, true>(op->n, op->L, op->PW, &smem, &W, accg)
                          : pick_threads<LOGM, false>(op->n, op->L, 0, &smem, &W);
     if (smem > 227 * 1024) return fail(SB_EINVAL, "AMP: n too large for shared memory%s (%ld bytes)", "", (long)smem);
 #define SB_LAUNCH(KERNEL, ...)                                                                           \

@@ -157,7 +157,7 @@ class Operator:
         n_exec = torch.empty(B, dtype=I32, device=dev)
         flags = torch.empty(B, dtype=I32, device=dev)
         tau2 = torch.full((B, max(T, 1)), float("nan"), dtype=F64, device=dev) if trace else None
-        scratch = torch.empty((B, self.n), dtype=F64, device=dev) if mode == "fast" else None
+        scratch = torch.empty((2, B, self.n), dtype=F64, device=dev) if mode == "fast" else None
         check(_lib.lib().sb_amp_batch(self._h, _p(y), _p(Pl), _p(beta0), _p(sections), _p(nsec), B, int(T), _MODES[mode],
                                       _p(beta), _p(iters), _p(n_exec), _p(flags), _p(tau2), _p(scratch), _stream()),
               "sb_amp_batch")
