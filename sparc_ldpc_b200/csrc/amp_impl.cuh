@@ -382,7 +382,7 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
         for (int e = 0; e < EPT; e++) {
             double b;
             if constexpr (TRQ) b = bv[e];
-            else b = first_zero ? 0.0 : bsrc[e * TEAM + q];
+            else b = first_zero ? 0.0 : __ldcs(bsrc + e * TEAM + q);  // streamed once per iteration
             const double s = b + x[e] * cx.inv_rt_n;  // s = beta + A^T z          (sparc_ldpc.py:213)
             x[e] = s * c2;                            // u = s sqrt(n P_l)/tau^2    (:215)
             m = fmax(m, x[e]);
@@ -404,8 +404,7 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
         for (int e = 0; e < EPT; e++) {
             x[e] *= sc;  // beta = sqrt(n P_l) softmax(u)    (:218-219)
             sq += x[e] * x[e];
-            if constexpr (TRQ) __stcs(bdst + e * TEAM + q, x[e]);
-            else bdst[e * TEAM + q] = x[e];
+            __stcs(bdst + e * TEAM + q, x[e]);
         }
         SB_CLK(a, 3);
     } else {
