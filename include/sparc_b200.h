@@ -49,8 +49,10 @@ extern "C" {
 
 /* per-codeword status bits written by sb_amp_batch into flags[b] */
 #define SB_AMP_STOPPED 1u   /* tau == last_tau fired (sparc_ldpc.py:204)                        */
-#define SB_AMP_REF_NAN 2u   /* the reference's global-max softmax (sparc_ldpc.py:216-219) would
-                               have produced 0/0 in at least one section on this codeword        */
+#define SB_AMP_REF_NAN 2u   /* the reference's global-max softmax (sparc_ldpc.py:216-219) left fp64's normal range
+                               on this codeword: some section's maximum lay > 708.4 below the global one (sums of
+                               subnormals, relative error ~1e-5) or > 745.1 below it (0/0 = NaN); the kernel itself
+                               computes every section accurately */
 
 const char *sb_last_error(void);
 int sb_version(void);

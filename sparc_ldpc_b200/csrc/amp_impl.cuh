@@ -864,7 +864,9 @@ __global__ void __launch_bounds__(512, 1) amp_kernel(AmpArgs a, int W) {
         const double sumsq = block_sum(sq, red);
         const double gm = block_max(gmax, red);
         const double lm = -block_max(-lmin, red);
-        if (gm - lm > 745.13) flags |= SB_AMP_REF_NAN;
+        // the reference subtracts the GLOBAL maximum (:216): a section whose maximum lies more than -log(DBL_MIN) =
+        // 708.4 below it is summed in subnormals (relative error up to ~1e-5 observed) and, beyond 745.1, is 0/0
+        if (gm - lm > 708.39) flags |= SB_AMP_REF_NAN;
         const double ons = P - sumsq / nd;  // (:220)
         for (int k = threadIdx.x; k < n; k += blockDim.x) zf[k] = (y[k] - acc_s[k] / rt_n) + (zf[k] / cx.tau2) * ons;
         __syncthreads();

@@ -307,6 +307,21 @@ def test_gaussian_column_sharded_matches_unsharded(Eng, oracle):
         assert e_ref < NORTH_STAR_RTOL and e_full < NORTH_STAR_RTOL
 
 
+def test_randomised_shapes_against_oracle():
+    """tools/fuzz_parity.py: 150 random (L, M, rate, power allocation, noise, prior) cases, STRICT to 1e-9 and FAST to
+    2e-6 of the oracle; the three documented exception classes (reference softmax underflow, non-convergent AMP,
+    early FAST stop) are re-checked at equal iteration counts.  Exits non-zero on any other deviation."""
+    import os
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "--cases", "150", "--seed", "3",
+                        "--budget-s", "90"], capture_output=True, text=True, timeout=300)
+    print(r.stdout[-1200:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "fuzz:" in r.stdout
+
+
 def test_gaussian_column_sharded_peer_memory_exchange():
     """The column-sharded decode with the exchange over peer memory (sb_dense_amp_batch_p2p): every shard pushes its
     partial A beta into a slot of every peer's receive area, publishes an epoch flag, waits for the peers' flags and
