@@ -322,6 +322,19 @@ def test_randomised_shapes_against_oracle():
     assert "fuzz:" in r.stdout
 
 
+def test_handoff_kernels_all_lanes_equal_one_warp_per_section():
+    """tools/fuzz_handoff.py: sp2bp_llr_kernel16 / bp2sp_prior_kernel512 against the one-warp-per-section kernels on
+    120 random cases (M = 64..1024, offsets, ragged section lists, one-hot / saturated sections): bit-identical."""
+    import os
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "tools", "fuzz_handoff.py"), "1"], capture_output=True, text=True,
+                       timeout=300)
+    print(r.stdout[-600:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_gaussian_column_sharded_peer_memory_exchange():
     """The column-sharded decode with the exchange over peer memory (sb_dense_amp_batch_p2p): every shard pushes its
     partial A beta into a slot of every peer's receive area, publishes an epoch flag, waits for the peers' flags and
