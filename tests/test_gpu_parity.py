@@ -322,6 +322,19 @@ def test_randomised_shapes_against_oracle():
     assert "fuzz:" in r.stdout
 
 
+def test_bp_all_code_families_random_z():
+    """tools/fuzz_bp.py: every protograph family of the code tables at two random lifting sizes, noisy LLRs, GPU BP
+    (strict, fast) against the CPU oracle: iteration counts, decisions and app of convergent blocks."""
+    import os
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "tools", "fuzz_bp.py"), "1"], capture_output=True, text=True,
+                       timeout=400)
+    print(r.stdout[-600:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_handoff_kernels_all_lanes_equal_one_warp_per_section():
     """tools/fuzz_handoff.py: sp2bp_llr_kernel16 / bp2sp_prior_kernel512 against the one-warp-per-section kernels on
     120 random cases (M = 64..1024, offsets, ragged section lists, one-hot / saturated sections): bit-identical."""
