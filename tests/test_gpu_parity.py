@@ -335,6 +335,21 @@ def test_bp_all_code_families_random_z():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_link_sims_random_small_shapes():
+    """tools/fuzz_flows.py: the four link simulations at 150 random small (L, M, z, rate, sigma, flow) with the
+    reference's RNG draw order -> BER tuples identical to the oracle's, except in the three platform-dependent classes
+    the tool names (non-convergent BP, NaN overflow of the reference's BP on saturated LLRs, saturated / erased
+    LLRs), where ours must be within 3 bits or not worse than the reference at any stage."""
+    import os
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "tools", "fuzz_flows.py"), "2", "150"], capture_output=True,
+                       text=True, timeout=400)
+    print(r.stdout[-900:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_handoff_kernels_all_lanes_equal_one_warp_per_section():
     """tools/fuzz_handoff.py: sp2bp_llr_kernel16 / bp2sp_prior_kernel512 against the one-warp-per-section kernels on
     120 random cases (M = 64..1024, offsets, ragged section lists, one-hot / saturated sections): bit-identical."""
