@@ -17,6 +17,7 @@ _MODES = {"strict": _lib.SB_AMP_STRICT, "fast": _lib.SB_AMP_FAST}
 # Default arithmetic of Operator.amp.  "strict" = fp64 in the reference's order of additions (parity mode);
 # "fast" = 32-bit fixed-point gathers.  Override per call with mode=..., or globally
 # with the environment variable SPARC_B200_AMP_MODE.
+import ctypes as _ct
 import os as _os
 AMP_MODE = _os.environ.get("SPARC_B200_AMP_MODE", "strict")
 # Default arithmetic of Graph.bp for dectype "sumprod2": "strict" = fp64 exp/log as c_ldpc.c:246-247; "fast" = the
@@ -307,14 +308,15 @@ class DenseOperator:
         return AmpResult(beta, iters, n_exec, flags, tau2)
 
 
+class _SbP2p(_ct.Structure):
+    """struct sb_p2p of include/sparc_b200.h"""
+    _fields_ = [("rank", _ct.c_int), ("world", _ct.c_int), ("timeout_ms", _ct.c_int),
+                ("slots", _ct.c_void_p * 8), ("flags", _ct.c_void_p * 8)]
+
+
 class PeerExchange:
     """Receive areas ([2][world][B n + B] doubles) and flag words ([world] uint64) of every rank of a column-sharded
     dense operator, mapped into this process (include/sparc_b200.h sb_p2p)."""
-
-    class _C(__import__("ctypes").Structure):
-        import ctypes as _ct
-        _fields_ = [("rank", _ct.c_int), ("world", _ct.c_int), ("timeout_ms", _ct.c_int),
-                    ("slots", _ct.c_void_p * 8), ("flags", _ct.c_void_p * 8)]
 
     def __init__(self, rank, world, slot_doubles, areas, flagws, timeout_ms=20000):
         import ctypes as ct
@@ -322,7 +324,7 @@ class PeerExchange:
             raise ValueError("at most 8 ranks (one NVSwitch domain)")
         self.rank, self.world, self.slot_doubles = rank, world, slot_doubles
         self._keep = (areas, flagws)          # the mapped tensors must outlive the exchange
-        self.cstruct = PeerExchange._C()
+        self.cstruct = _SbP2p()
         self.cstruct.rank, self.cstruct.world, self.cstruct.timeout_ms = rank, world, int(timeout_ms)
         for r in range(world):
             self.cstruct.slots[r] = areas[r].data_ptr()
@@ -336,7 +338,9 @@ class PeerExchange:
 
     @staticmethod
     def in_process(world, B, n, dev=None):
-        """All ranks live in this process (threads, one stream each, same or different GPUs of the process)."""
+        """All ranks live in this process (threads, one stream each).  Only safe when the ranks' streams never share a
+        hardware queue and no thread allocates device memory while a peer spins on its flag (use amp_p2p's
+        before_launch rendezvous); separate processes (from_process_group) have neither restriction."""
         dev = dev or _dev()
         allocs = [PeerExchange._alloc(world, B, n, dev) for _ in range(world)]
         areas, flagws = [a[1] for a in allocs], [a[2] for a in allocs]
