@@ -96,6 +96,10 @@ void sb_operator_destroy(sb_operator *op);
  * stats[4] (may be NULL) = fold steps, fold shared-memory wavefronts, gather steps, gather wavefronts of the
  * bank-conflict model.  Returns 0 = verified, 1 = shape has no FAST tables, <0 = error. */
 int sb_fast_tables_check(const uint32_t *ordering_host, int L, int M, int n, long *stats);
+/* The same self check for the tables of the two-codewords-per-CTA FAST kernel (M = 512, w/M <= 16, n <= 4608,
+ * L % 8 == 0; csrc/amp2.cu): every (bin, sign half) lists exactly its rows, every (8-section group, row) its 8
+ * (section, column, sign) terms.  Returns 0 = verified, 1 = the shape has no pair tables, <0 = error. */
+int sb_pair_tables_check(const uint32_t *ordering_host, int L, int M, int n, long *stats);
 
 /* pyfht.fht_inplace (sparc_ldpc.py:14-29, :69, :76): HOST pointer, N a power of two, transformed in place. */
 int sb_fht_inplace_host(double *x, long N);
@@ -126,6 +130,11 @@ int sb_onehot_apply_batch(const sb_operator *op, const int *idx, const double *P
                            z update and tau^2 stay fp64.  beta / tau^2 agree with STRICT to ~1e-8 relative.  The
                            stop rule becomes |tau - last_tau| <= 2^-27 tau (tau cannot reach an exact fixed point
                            above the quantisation floor), so `iters` is smaller than in STRICT mode.                */
+/* FAST mode has two kernels: one CTA per codeword (any shape) and, for M = 512 with w/M <= 16, n <= 4608, L % 8 == 0
+ * and all sections active, a warp-specialised kernel that decodes two codewords per CTA (csrc/amp2.cu; same
+ * arithmetic, A beta / A^T z bit-identical).  sb_amp_pair_enable(0) forces the first for every shape (A/B timing,
+ * parity tests); returns the previous setting. */
+int sb_amp_pair_enable(int on);
 int sb_amp_batch(const sb_operator *op, const double *y, const double *Pl, const double *beta0, const int *sections,
                  const int *nsec, int B, int T, int mode, double *beta, int *iters, int *n_exec, unsigned *flags,
                  double *tau2_trace, double *scratch /* [2][B][n] work space, required in FAST mode: z and, for n > 8191,

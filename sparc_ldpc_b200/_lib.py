@@ -37,10 +37,12 @@ SIGNATURES = {
     "sb_operator_create": (_i, [_vp, _i, _i, _i, ct.POINTER(_vp)]),
     "sb_operator_destroy": (None, [_vp]),
     "sb_fast_tables_check": (_i, [_vp, _i, _i, _i, _vp]),
+    "sb_pair_tables_check": (_i, [_vp, _i, _i, _i, _vp]),
     "sb_fht_inplace_host": (_i, [_vp, _l]),
     "sb_Ab_batch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "sb_Az_batch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "sb_onehot_apply_batch": (_i, [_vp, _vp, _vp, _vp, _d, _i, _vp, _vp]),
+    "sb_amp_pair_enable": (_i, [_i]),
     "sb_amp_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_sp2bp_llr_batch": (_i, [_vp, _l, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _l, _vp]),
     "sb_bp2sp_prior_batch": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),

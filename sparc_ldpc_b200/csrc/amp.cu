@@ -190,8 +190,7 @@ static void build_fast_tables(const uint32_t *ordering, int L, int M, int n, int
                                              (fq_word(logM, lo) << 2) + (sg << SBQ);
                         E.push_back(PoolEdge{q, (int)((off >> 2) & 31), (int)off, 0});
                     }
-                ps.run(E, PW);
-                PoolScheduler::improve(E, PW);
+                ps.run_best(E, PW);
                 gstat[(size_t)g * 2] += PW;
                 gstat[(size_t)g * 2 + 1] += PoolScheduler::cost(E, PW);
                 for (const PoolEdge &pe : E)
@@ -200,6 +199,89 @@ static void build_fast_tables(const uint32_t *ordering, int L, int M, int n, int
     });
     for (int g = 0; g < ft.GQ; g++) { ft.gather_steps += gstat[(size_t)g * 2]; ft.gather_wavefronts += gstat[(size_t)g * 2 + 1]; }
 }
+
+
+// ---- pair-kernel tables (amp2.cu: two codewords per CTA, M = 512, w/M <= 16, n <= 4608, L % 8 == 0) ---------
+// The same two maps as build_fast_tables with three differences: (1) there is no -z / -F copy: the fold's sign is
+// the HALF of the bin's 16 steps an entry sits in (steps 0..7 are added, 8..15 subtracted; a bin has at most 8
+// blocks of each parity when w/M <= 16), the gather's sign is bit 15 of the entry; (2) a gather chunk is 8
+// sections: entry = slot * 4096 + fq_word(lo) * 4 | sign << 15, the byte offset of codeword 0's word inside the
+// group buffer [8 slots][2 codewords][512 int32] (codeword 1 sits 2048 bytes further); (3) fold entries are byte
+// offsets into one codeword's z plane [n values | 32 zero words].
+struct PairTables {
+    int ok = 0;
+    std::vector<uint16_t> inv2, fwd2;
+    long fold_steps = 0, fold_wavefronts = 0, gather_steps = 0, gather_wavefronts = 0;
+};
+
+static bool pair_shape_ok(int L, int M, int n, int H) { return M == 512 && H <= 16 && n <= 4608 && n >= 32 && L % 8 == 0; }
+
+static void build_pair_tables(const uint32_t *ordering, int L, int M, int n, int H, PairTables &pt) {
+    if (!pair_shape_ok(L, M, n, H)) return;
+    pt.ok = 1;
+    const int logM = 9, TEAM = 32, EPT = 16;
+    pt.inv2.assign((size_t)L * M * 16, 0);
+    std::vector<long> stat((size_t)L * 2, 0);
+    parallel_for(L, [&](int l0, int l1) {
+        PoolScheduler ps;
+        std::vector<PoolEdge> E;
+        std::vector<std::vector<int>> bins(2 * M);  // [sign][bin]
+        std::vector<int> used(8 * 32);
+        for (int l = l0; l < l1; l++) {
+            for (auto &b : bins) b.clear();
+            for (int k = 0; k < n; k++) {
+                const uint32_t r = ordering[(size_t)l * n + k];
+                bins[(size_t)(__builtin_popcount(r / M) & 1) * M + r % M].push_back(k);
+            }
+            for (int e = 0; e < EPT; e++)
+                for (int sg = 0; sg < 2; sg++) {
+                    E.clear();
+                    for (int q = 0; q < TEAM; q++)
+                        for (int k : bins[(size_t)sg * M + fast_bin(logM, TEAM, e, q)]) E.push_back(PoolEdge{q, k & 31, k, 0});
+                    ps.run_best(E, 8);
+                    stat[(size_t)l * 2] += 8;
+                    stat[(size_t)l * 2 + 1] += PoolScheduler::cost(E, 8);
+                    std::fill(used.begin(), used.end(), 0);
+                    for (const PoolEdge &pe : E) used[(size_t)pe.step * 32 + pe.bank] = 1;
+                    uint16_t *dst = pt.inv2.data() + (((size_t)l * EPT + e) * 2 + sg) * TEAM * 8;
+                    for (int t = 0; t < 8; t++) {  // idle slots read a zero word in a bank no real term of the step uses
+                        int fb = 0;
+                        for (int b = 0; b < 32; b++) if (!used[(size_t)t * 32 + b]) { fb = b; break; }
+                        const int zero_word = n + ((fb - n) & 31);
+                        for (int q = 0; q < TEAM; q++) dst[q * 8 + t] = (uint16_t)(zero_word * 4);
+                    }
+                    for (const PoolEdge &pe : E) dst[pe.lane * 8 + pe.step] = (uint16_t)(pe.id * 4);
+                }
+        }
+    });
+    for (int l = 0; l < L; l++) { pt.fold_steps += stat[(size_t)l * 2]; pt.fold_wavefronts += stat[(size_t)l * 2 + 1]; }
+    const int G = L / 8;
+    pt.fwd2.assign((size_t)G * n * 8, 0);
+    std::vector<long> gstat((size_t)G * 2, 0);
+    parallel_for(G, [&](int g0, int g1) {
+        PoolScheduler ps;
+        std::vector<PoolEdge> E;
+        for (int g = g0; g < g1; g++)
+            for (int k0 = 0; k0 < n; k0 += 32) {
+                E.clear();
+                const int nl = (n - k0 < 32) ? n - k0 : 32;
+                for (int q = 0; q < nl; q++)
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t r = ordering[(size_t)(g * 8 + i) * n + k0 + q];
+                        const uint32_t lo = r % M, sg = __builtin_popcount(r / M) & 1;
+                        const uint32_t off = (uint32_t)i * 4096u + (fq_word(logM, lo) << 2);
+                        E.push_back(PoolEdge{q, (int)((off >> 2) & 31), (int)(off | (sg << 15)), 0});
+                    }
+                ps.run_best(E, 8);
+                gstat[(size_t)g * 2] += 8;
+                gstat[(size_t)g * 2 + 1] += PoolScheduler::cost(E, 8);
+                for (const PoolEdge &pe : E) pt.fwd2[((size_t)g * n + k0 + pe.lane) * 8 + pe.step] = (uint16_t)pe.id;
+            }
+    });
+    for (int g = 0; g < G; g++) { pt.gather_steps += gstat[(size_t)g * 2]; pt.gather_wavefronts += gstat[(size_t)g * 2 + 1]; }
+}
+
+int launch_amp2(const sb_operator *op, const AmpArgs &a, int B, cudaStream_t st);  // amp2.cu
 
 }  // namespace sb
 
@@ -254,9 +336,24 @@ extern "C" int sb_operator_create(const uint32_t *ordering, int L, int M, int n,
             }
         }
     }
+    op->p2ok = 0; op->inv2 = nullptr; op->fwd2 = nullptr;
+    if (op->qok) {  // pair-kernel tables
+        PairTables pt;
+        build_pair_tables(ordering, L, M, n, op->H, pt);
+        if (pt.ok) {
+            cudaError_t q1 = cudaMalloc(&op->inv2, pt.inv2.size() * 2), q2 = cudaMalloc(&op->fwd2, pt.fwd2.size() * 2);
+            if (q1 == cudaSuccess) q1 = cudaMemcpy(op->inv2, pt.inv2.data(), pt.inv2.size() * 2, cudaMemcpyHostToDevice);
+            if (q2 == cudaSuccess) q2 = cudaMemcpy(op->fwd2, pt.fwd2.data(), pt.fwd2.size() * 2, cudaMemcpyHostToDevice);
+            if (q1 != cudaSuccess || q2 != cudaSuccess) {
+                cudaFree(op->inv2); cudaFree(op->fwd2); cudaFree(op->invq); cudaFree(op->fwdq); free(hf); free(hi); free(h8); delete op;
+                return fail(SB_ENOMEM, "sb_operator_create: cudaMalloc (pair tables) failed%s", "");
+            }
+            op->p2ok = 1;
+        }
+    }
     cudaError_t e1 = cudaMalloc(&op->fwd, nf * 2), e2 = cudaMalloc(&op->inv, ni * 2), e3 = cudaMalloc(&op->fwd8, n8 * 2);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-        cudaFree(op->fwd); cudaFree(op->inv); cudaFree(op->fwd8); cudaFree(op->invq); cudaFree(op->fwdq);
+        cudaFree(op->fwd); cudaFree(op->inv); cudaFree(op->fwd8); cudaFree(op->invq); cudaFree(op->fwdq); cudaFree(op->inv2); cudaFree(op->fwd2);
         free(hf); free(hi); free(h8); delete op;
         return fail(SB_ENOMEM, "sb_operator_create: cudaMalloc failed%s", "");
     }
@@ -276,7 +373,57 @@ extern "C" void sb_operator_destroy(sb_operator *op) {
     cudaFree(op->inv);
     cudaFree(op->invq);
     cudaFree(op->fwdq);
+    cudaFree(op->inv2);
+    cudaFree(op->fwd2);
     delete op;
+}
+
+// Test hook (no GPU needed) for the pair-kernel tables: every (bin, sign half) of every section lists exactly its
+// rows, every (8-section group, row) exactly its 8 (slot, column, sign) terms.  stats[0..3] as sb_fast_tables_check.
+// Returns 0 = verified, 1 = the shape has no pair tables, < 0 = error.
+extern "C" int sb_pair_tables_check(const uint32_t *ordering, int L, int M, int n, long *stats) {
+    if (!ordering || L <= 0 || n <= 0 || M < 2 || (M & (M - 1)) || M > 1024 || n >= 65534)
+        return fail(SB_EINVAL, "sb_pair_tables_check: bad shape%s (M=%ld)", "", M);
+    int w = 1;
+    while (w < (M + 1 > n + 1 ? M + 1 : n + 1)) w <<= 1;
+    PairTables pt;
+    build_pair_tables(ordering, L, M, n, w / M, pt);
+    if (stats) { stats[0] = pt.fold_steps; stats[1] = pt.fold_wavefronts; stats[2] = pt.gather_steps; stats[3] = pt.gather_wavefronts; }
+    if (!pt.ok) return 1;
+    std::vector<int> seen(n);
+    for (int l = 0; l < L; l++) {
+        std::fill(seen.begin(), seen.end(), 0);
+        for (int e = 0; e < 16; e++)
+            for (int sg = 0; sg < 2; sg++)
+                for (int q = 0; q < 32; q++)
+                    for (int t = 0; t < 8; t++) {
+                        const int o = pt.inv2[((((size_t)l * 16 + e) * 2 + sg) * 32 + q) * 8 + t];
+                        if (o & 3) return fail(SB_EINVAL, "pair tables: unaligned fold offset%s (%ld)", "", o);
+                        const int k = o >> 2;
+                        if (k >= n && k < n + 32) continue;  // zero word
+                        if (k >= n + 32) return fail(SB_EINVAL, "pair tables: fold offset out of range%s (%ld)", "", o);
+                        const uint32_t r = ordering[(size_t)l * n + k];
+                        if ((int)(r % M) != fast_bin(9, 32, e, q) || (__builtin_popcount(r / M) & 1) != sg || seen[k]++)
+                            return fail(SB_EINVAL, "pair tables: wrong fold term%s (section %ld)", "", l);
+                    }
+        for (int k = 0; k < n; k++) if (seen[k] != 1) return fail(SB_EINVAL, "pair tables: missing fold term%s (section %ld)", "", l);
+    }
+    for (int g = 0; g < L / 8; g++)
+        for (int k = 0; k < n; k++) {
+            unsigned mask = 0;
+            for (int t = 0; t < 8; t++) {
+                const uint32_t e = pt.fwd2[((size_t)g * n + k) * 8 + t];
+                const uint32_t sg = e >> 15, off = e & 0x7FFFu, slot = off >> 12, word = (off & 4095u) >> 2;
+                if ((off & 3) || word >= 512) return fail(SB_EINVAL, "pair tables: bad gather offset%s (%ld)", "", e);
+                const uint32_t lo = ((word >> 1) & 15u) * 32u + 2u * (word >> 5) + (word & 1u);  // inverse of fq_word
+                const uint32_t r = ordering[(size_t)(g * 8 + slot) * n + k];
+                if (r % M != lo || (uint32_t)(__builtin_popcount(r / M) & 1) != sg)
+                    return fail(SB_EINVAL, "pair tables: wrong gather term%s (group %ld)", "", g);
+                mask |= 1u << slot;
+            }
+            if (mask != 0xFFu) return fail(SB_EINVAL, "pair tables: missing gather term%s (group %ld)", "", g);
+        }
+    return SB_OK;
 }
 
 // Test hook (no GPU needed): builds the FAST-mode tables on the host and verifies that they are a reordering of
@@ -350,6 +497,11 @@ extern "C" int sb_phase_cycles_read(unsigned long long *out16) {
 }
 #endif
 
+// Diagnostic switch (A/B timing and the pair-vs-single parity test): 0 makes FAST mode use the one-codeword-per-CTA
+// kernel for every shape.  Returns the previous setting.  Initial value: 1, or 0 when SB_AMP_PAIR=0 is set.
+static std::atomic<int> g_pair_on{[] { const char *e = getenv("SB_AMP_PAIR"); return (e && e[0] == '0') ? 0 : 1; }()};
+extern "C" int sb_amp_pair_enable(int on) { return g_pair_on.exchange(on ? 1 : 0); }
+
 extern "C" int sb_amp_batch(const sb_operator *op, const double *y, const double *Pl, const double *beta0,
                             const int *sections, const int *nsec, int B, int T, int mode, double *beta, int *iters,
                             int *n_exec, unsigned *flags, double *tau2_trace, double *scratch, void *stream) {
@@ -367,6 +519,8 @@ extern "C" int sb_amp_batch(const sb_operator *op, const double *y, const double
     if (!g_dbg) { SB_CUDA(cudaMalloc(&g_dbg, 16 * sizeof(unsigned long long))); SB_CUDA(cudaMemset(g_dbg, 0, 16 * sizeof(unsigned long long))); }
     a.dbg = g_dbg;
 #endif
+    // FAST, all sections active, M = 512: the warp-specialised two-codeword kernel (amp2.cu)
+    if (mode == SB_AMP_FAST && op->p2ok && sections == nullptr && g_pair_on.load()) return launch_amp2(op, a, B, (cudaStream_t)stream);
     return dispatch(op, a, B, mode == SB_AMP_FAST ? 3 : 0, nullptr, nullptr, (cudaStream_t)stream);
 }
 

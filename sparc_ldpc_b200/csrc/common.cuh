@@ -86,6 +86,10 @@ struct sb_operator {
     int PW, GQ;           // gather pool = PW (8 | 16) sections; GQ = floor(L / PW) chunks in fwdq
     uint16_t *invq;       // [L][EPT][Hp/8][TEAM][8]  word (or byte) offset into [ +z (n) | 32 zero words | -z (n) ]
     uint16_t *fwdq;       // [GQ][PW/8][n][8]         byte offset into the +-F area of a PW-section chunk (logM <= 9)
+    // pair kernel (amp2.cu; M = 512, w/M <= 16, n <= 4608, L % 8 == 0): two codewords per CTA share every table word
+    int p2ok;
+    uint16_t *inv2;       // [L][16][2 signs][32][8]  byte offset into one codeword's z plane [n | 32 zero words]
+    uint16_t *fwd2;       // [L/8][n][8]              slot*4096 + word*4 | sign << 15 inside an 8-section group buffer
 };
 
 struct sb_graph {

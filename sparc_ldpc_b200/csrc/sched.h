@@ -11,6 +11,8 @@
 // hit at most once per step, and a bank of degree d > K at most ceil(d/K) times.
 #pragma once
 #include <stdint.h>
+#include <algorithm>
+#include <functional>
 #include <vector>
 
 namespace sb {
@@ -103,7 +105,89 @@ class PoolScheduler {
         }
     }
 
+    // Second heuristic: fill the steps one after the other, each with the smallest bank multiplicity c that still
+    // serves every lane that must read in this step (a lane with as many terms left as steps left), found by
+    // augmenting paths (lanes x banks with capacity c, banks with the most terms left first); lanes with slack join
+    // as long as c does not grow.  Early steps become conflict-free (perfect matchings take one term off EVERY bank),
+    // the excess of the heavy banks collects in the few last steps: sum_t c_t approaches its lower bound max_b
+    // degree(b), where the equitable colouring pays ceil(d/K) in (nearly) every step.
+    void run_greedy(std::vector<PoolEdge> &E, int K) {
+        const int m = (int)E.size();
+        int reml[32] = {0}, remb[32] = {0}, match[32], order[32], nat[32];
+        alive_.assign(m, 1);
+        for (const PoolEdge &e : E) { reml[e.lane]++; remb[e.bank]++; }
+        for (auto &v : adj_) v.clear();
+        for (int i = 0; i < m; i++) adj_[E[i].lane].push_back(i);
+        for (int t = 0; t < K; t++) {
+            const int left = K - t;
+            for (int l = 0; l < 32; l++) {  // this step's candidate edges of every lane, banks with the most terms left first
+                cand_[l].clear();
+                for (int i : adj_[l]) if (alive_[i]) cand_[l].push_back(i);
+                std::sort(cand_[l].begin(), cand_[l].end(), [&](int x, int y) { return remb[E[x].bank] > remb[E[y].bank]; });
+                order[l] = l;
+            }
+            std::sort(order, order + 32, [&](int x, int y) { return reml[x] > reml[y]; });
+            for (cap_ = 1;; cap_++) {
+                for (int l = 0; l < 32; l++) { match[l] = -1; nat[l] = 0; }
+                bool ok = true;
+                for (int oi = 0; oi < 32 && ok; oi++) {
+                    const int l = order[oi];
+                    if (reml[l] < left) break;  // (sorted: the rest has slack)
+                    vis_ = 0;
+                    ok = aug(E, l, match, nat);
+                }
+                if (ok) break;
+            }
+            for (int oi = 0; oi < 32; oi++) {  // lanes with slack: as many as fit without raising the multiplicity
+                const int l = order[oi];
+                if (reml[l] >= left || reml[l] == 0) continue;
+                vis_ = 0;
+                aug(E, l, match, nat);
+            }
+            for (int l = 0; l < 32; l++) {
+                const int i = match[l];
+                if (i < 0) continue;
+                E[i].step = t;
+                alive_[i] = 0;
+                reml[l]--;
+                remb[E[i].bank]--;
+            }
+        }
+    }
+
+    // the cheaper of the two schedules under the wavefront model
+    void run_best(std::vector<PoolEdge> &E, int K) {
+        run(E, K);
+        improve(E, K);
+        const int c1 = cost(E, K);
+        std::vector<PoolEdge> G = E;
+        run_greedy(G, K);
+        if (cost(G, K) < c1) E.swap(G);
+    }
+
   private:
+    // augmenting path for lane u: banks hold up to cap_ lanes (at_[b][0..nat[b]))
+    bool aug(const std::vector<PoolEdge> &E, int u, int *match, int *nat) {
+        for (int i : cand_[u]) {
+            const int b = E[i].bank;
+            if (vis_ & (1u << b)) continue;
+            vis_ |= 1u << b;
+            if (nat[b] < cap_) { at_[b][nat[b]++] = u; match[u] = i; return true; }
+            for (int k = 0; k < nat[b]; k++) {
+                const int w = at_[b][k];
+                if (aug(E, w, match, nat)) {  // w moved to another bank (its entry in at_[b] is still at index k)
+                    at_[b][k] = u;
+                    match[u] = i;
+                    return true;
+                }
+            }
+        }
+        return false;
+    }
+    std::vector<int> alive_, adj_[32], cand_[32];
+    int at_[32][32];
+    unsigned vis_ = 0;
+    int cap_ = 1;
     std::vector<int> idx_, tmp_, label_, head_, nxt_, other_;
     std::vector<char> used_;
 

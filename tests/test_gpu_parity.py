@@ -851,3 +851,69 @@ def test_exit_histogram_semantics(Eng):
         for w, s in ((0, 1), (1, -1)):
             ref, _ = np.histogram(Ev[b][X[b] == s], bins=edges)
             assert np.array_equal(cnt[b, w], ref)
+
+
+# ------------------------------------------------------------------------------------------- pair kernel (amp2.cu)
+@pytest.mark.parametrize("shape", [(512, 512, 4608), (48, 512, 432), (64, 512, 1150)])
+def test_pair_kernel_equals_single_codeword_fast_kernel(Eng, S, shape):
+    """FAST mode at M = 512 runs the warp-specialised two-codewords-per-CTA kernel (csrc/amp2.cu).  Its integer
+    gathers are order-free, so it must reproduce the one-codeword-per-CTA FAST kernel: same iteration counts and
+    flags, beta / tau^2 equal to fp64 summation-order noise -- for a zero start, a beta0 start, odd batches, a
+    batch of one, batches larger than the grid (work queue) and T = 0."""
+    from sparc_ldpc_b200 import _lib
+    L, M, n = shape
+    T = 40
+    rng = np.random.RandomState(7)
+    Pl = 4.0 / L * np.ones(L)
+    op = Eng.get_operator(L, M, n, 0)
+    Pld = cu(Pl)
+    nb = 301 if L <= 64 else 7
+    idx = rng.randint(0, M, size=(nb, L)).astype(np.int32)
+    tx = torch.from_numpy(idx).cuda()
+    # spread of noise levels: some codewords stop early, some run all T iterations
+    sig = np.linspace(0.5, 1.5, nb)[:, None]
+    y = op.onehot_apply(tx, Pld) + cu(sig * rng.randn(nb, n))
+    prior = rng.rand(nb, L, M) ** 8
+    prior /= prior.sum(axis=2, keepdims=True)
+    b0 = cu((prior * np.sqrt(n * Pl)[None, :, None]).reshape(nb, L * M))
+    lib = _lib.lib()
+
+    def run(pair, yy, beta0, t):
+        prev = lib.sb_amp_pair_enable(int(pair))
+        try:
+            r = op.amp(yy, Pld, t, beta0=beta0, trace=True, mode="fast")
+            torch.cuda.synchronize()
+        finally:
+            lib.sb_amp_pair_enable(prev)
+        return r
+
+    # short decodes: fp64 summation-order noise (1e-16 per iteration) has no room to grow -> tight comparison
+    for sl, use_b0, t in ((slice(0, nb), False, 6), (slice(0, nb), True, 6), (slice(0, 1), False, 6),
+                          (slice(1, 4), True, 5), (slice(0, 2), False, 0), (slice(0, 3), True, 0)):
+        yy = y[sl].contiguous()
+        bb = b0[sl].contiguous() if use_b0 else None
+        a, b = run(True, yy, bb, t), run(False, yy, bb, t)
+        assert a.iters.tolist() == b.iters.tolist() and a.n_exec.tolist() == b.n_exec.tolist()
+        assert a.flags.tolist() == b.flags.tolist()
+        if t:
+            ta, tb = a.tau2.cpu().numpy(), b.tau2.cpu().numpy()
+            m = ~np.isnan(tb)
+            assert np.array_equal(np.isnan(ta), np.isnan(tb))
+            assert relinf(ta[m], tb[m]) < 1e-10
+        err = relinf(a.beta.cpu().numpy().reshape(-1), b.beta.cpu().numpy().reshape(-1))
+        print("pair vs single %s b0=%s T=%d: max rel beta diff %.2e" % (shape, use_b0, t, err))
+        assert err < 1e-9
+    # full-length decodes: early stops at different iterations per codeword exercise the slot refill; codewords
+    # that converge must stop at the same iteration with the same beta (non-convergent orbits amplify the
+    # summation-order noise and are compared on their first iterations above)
+    a, b = run(True, y, None, T), run(False, y, None, T)
+    ia, ib = np.array(a.iters.tolist()), np.array(b.iters.tolist())
+    conv = ib < T - 1
+    assert conv.sum() >= 1
+    same = conv & (ia == ib)   # (the tolerance stop |d tau| <= 2^-27 tau is itself a near-tie on slow orbits)
+    assert same.sum() >= 0.9 * conv.sum()
+    ba, bb_ = a.beta.cpu().numpy()[same], b.beta.cpu().numpy()[same]
+    err = relinf(ba.reshape(-1), bb_.reshape(-1))
+    print("pair vs single %s full decode: %d of %d converge, iterations %d..%d, max rel beta diff %.2e"
+          % (shape, conv.sum(), nb, ia.min(), ia.max(), err))
+    assert err < 1e-7

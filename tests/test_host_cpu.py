@@ -124,3 +124,22 @@ def test_fast_mode_tables_are_a_reordering_of_the_operator(shape):
     # a corrupted ordering entry (out of range) is rejected by the operator constructor's own checks, not here;
     # but a table built from a different ordering must not verify against this one -> exercised by the C check
     # itself (it compares every term with `ordering`)
+
+
+@pytest.mark.parametrize("shape", [(48, 512, 432), (16, 512, 144), (64, 512, 4608), (24, 512, 2300), (40, 512, 1000)])
+def test_pair_kernel_tables_are_a_reordering_of_the_operator(shape):
+    """Tables of the two-codewords-per-CTA FAST kernel (csrc/amp2.cu): fold terms listed by sign half, gather terms
+    with the sign in bit 15; must list exactly the operator's terms (host code, no GPU).  Shapes outside the
+    kernel's range report 1 (no pair tables)."""
+    import ctypes as ct
+    from sparc_ldpc_b200 import _lib
+    from sparc_ldpc_b200.engine import make_ordering
+    L, M, n = shape
+    o = make_ordering(L, M, n)
+    st = (ct.c_long * 4)()
+    rc = _lib.lib().sb_pair_tables_check(o.ctypes.data, L, M, n, st)
+    assert rc == 0, _lib.lib().sb_last_error()
+    assert st[0] > 0 and st[1] <= 1.3 * st[0] and st[3] <= 2.3 * st[2]
+    for L2, M2, n2 in ((20, 512, 180), (64, 256, 576), (16, 512, 6000)):   # L % 8, M != 512, w/M = 32
+        o2 = make_ordering(L2, M2, n2)
+        assert _lib.lib().sb_pair_tables_check(o2.ctypes.data, L2, M2, n2, None) == 1
