@@ -27,8 +27,11 @@
 #include "amp_impl.cuh"
 
 // experiment switches (tools/ab_build2.sh): defaults are the measured best
-#ifndef P2_FOLD_AHEAD
-#define P2_FOLD_AHEAD 1  // bins whose table words are in flight while one bin is reduced (1 | 2)
+#ifndef P2_FOLD_UNROLL
+#define P2_FOLD_UNROLL 2  // unroll factor of the fold's loop over the 16 bins of a lane (code size vs scheduling freedom)
+#endif
+#ifndef P2_TW_UNROLL
+#define P2_TW_UNROLL 1  // 1: one copy of the transform code for both slots; 2: one copy per slot
 #endif
 #ifndef P2_GATHER_DB
 #define P2_GATHER_DB 1  // gather table words double-buffered in batches of 3 rows (0: batches of 6, no overlap)
@@ -49,6 +52,20 @@
 namespace sb {
 namespace p2 {
 
+#ifdef P2_TRACE
+// experiment builds (tools/ab_build2.sh TAG -DP2_TRACE): thread 0 of every CTA logs (pass start, pass end, end of the
+// following iteration boundary) in ns and the slots' states; read with sb_p2_trace_read
+constexpr int TRACE_MAX = 1 << 20;
+__device__ unsigned long long g_trace[TRACE_MAX * 4];
+__device__ int g_trace_n;
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
+constexpr int FOLD_UNROLL = P2_FOLD_UNROLL, TW_UNROLL = P2_TW_UNROLL;
 constexpr int M = 512, S = 8;             // section size, sections per group
 constexpr int NOW = 256, NR = 18;         // operator threads, rows of A beta per operator thread
 constexpr int MAXN = NOW * NR;            // n <= 4608
@@ -112,57 +129,40 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 __device__ __forceinline__ int lds32(const char *p) { return *reinterpret_cast<const int *>(p); }
 
 // 8 table entries (16 bytes) of one bin half: sums of the two codewords' z words they address
+// (NC = 1: only the plane z0 points at -- the CTA's other slot is empty)
+template <int NC>
 __device__ __forceinline__ void fold8(const uint4 w, const char *z0, int &a0, int &a1) {
     const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const uint32_t lo = wd[i] & 0xFFFFu, hi = wd[i] >> 16;
         a0 += lds32(z0 + lo) + lds32(z0 + hi);
-        a1 += lds32(z0 + ZPLANE + lo) + lds32(z0 + ZPLANE + hi);
+        if (NC == 2) a1 += lds32(z0 + ZPLANE + lo) + lds32(z0 + ZPLANE + hi);
     }
 }
 
 // operator warp `rw` folds z of both codewords into the 512 bins of section l and leaves them in the section's
 // slot of the group buffer: word e*32+q of plane c = bin (q>>1)*32 + 2e + (q&1) (layout B of amp_impl.cuh)
+template <int NC>
 __device__ __forceinline__ void fold_section2(const uint16_t *__restrict__ inv2, int l, int q, const char *z0, char *slot) {
     const uint4 *t4 = reinterpret_cast<const uint4 *>(inv2) + (size_t)l * (16 * 2 * 32) + q;
-    int *st = reinterpret_cast<int *>(slot);
-    // table words of bins e+1 and e+2 are in flight while bin e is reduced (an operator warp has one partner warp
-    // per scheduler to hide the L2 latency behind)
-#if P2_FOLD_AHEAD == 2
-    uint4 c0 = __ldg(t4), c1 = __ldg(t4 + 32), n0 = __ldg(t4 + 64), n1 = __ldg(t4 + 96);
-#pragma unroll
-    for (int e = 0; e < 16; e++) {
-        uint4 f0 = n0, f1 = n1;
-        if (e + 2 < 16) {
-            f0 = __ldg(t4 + (2 * (e + 2)) * 32);
-            f1 = __ldg(t4 + (2 * (e + 2) + 1) * 32);
-        }
-        int p0 = 0, p1 = 0, m0 = 0, m1 = 0;
-        fold8(c0, z0, p0, p1);  // blocks of even parity: +
-        fold8(c1, z0, m0, m1);  // blocks of odd parity: -
-        st[e * 32 + q] = p0 - m0;
-        st[CWOFF / 4 + e * 32 + q] = p1 - m1;
-        c0 = n0; c1 = n1;
-        n0 = f0; n1 = f1;
-    }
-#else
+    int *st = reinterpret_cast<int *>(slot) + q;
+    // The table words of the next bin are in flight while one bin is reduced.  The loop over the 16 bins is NOT
+    // fully unrolled: the kernel's hot code has to fit the instruction caches (the SM's and the GPC's), see the
+    // note on code size at role_main.
     uint4 c0 = __ldg(t4), c1 = __ldg(t4 + 32);
-#pragma unroll
+#pragma unroll FOLD_UNROLL
     for (int e = 0; e < 16; e++) {
-        uint4 n0 = c0, n1 = c1;
-        if (e + 1 < 16) {
-            n0 = __ldg(t4 + (2 * (e + 1)) * 32);
-            n1 = __ldg(t4 + (2 * (e + 1) + 1) * 32);
-        }
+        const int en = (e + 1 < 16) ? e + 1 : e;  // (the last iteration reloads its own words: no branch)
+        const uint4 n0 = __ldg(t4 + (2 * en) * 32), n1 = __ldg(t4 + (2 * en + 1) * 32);
         int p0 = 0, p1 = 0, m0 = 0, m1 = 0;
-        fold8(c0, z0, p0, p1);  // blocks of even parity: +
-        fold8(c1, z0, m0, m1);  // blocks of odd parity: -
-        st[e * 32 + q] = p0 - m0;
-        st[CWOFF / 4 + e * 32 + q] = p1 - m1;
-        c0 = n0; c1 = n1;
+        fold8<NC>(c0, z0, p0, p1);  // blocks of even parity: +
+        fold8<NC>(c1, z0, m0, m1);  // blocks of odd parity: -
+        st[e * 32] = p0 - m0;
+        if (NC == 2) st[CWOFF / 4 + e * 32] = p1 - m1;
+        c0 = n0;
+        c1 = n1;
     }
-#endif
 }
 
 // prmt with a sign-replicating selector: every result byte = the msb of byte 1 (0x9999) or byte 3 (0xBBBB) of w
@@ -174,6 +174,7 @@ __device__ __forceinline__ int sign_mask(uint32_t w) {
 }
 
 // 8 entries of (group, row): signed words of both codewords' planes
+template <int NC>
 __device__ __forceinline__ void gather8(const uint4 w, const char *bufg, int &p0, int &p1) {
     const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
@@ -183,11 +184,11 @@ __device__ __forceinline__ void gather8(const uint4 w, const char *bufg, int &p0
         // +-1 from bit 15 / bit 31; the signed add is one IMAD on the (idle) fma pipe instead of XOR + IADD3 on the alu pipe
         const int slo = sign_mask<0x9999>(wd[i]) | 1, shi = sign_mask<0xBBBB>(wd[i]) | 1;
         p0 += lds32(bufg + olo) * slo + lds32(bufg + ohi) * shi;
-        p1 += lds32(bufg + CWOFF + olo) * slo + lds32(bufg + CWOFF + ohi) * shi;
+        if (NC == 2) p1 += lds32(bufg + CWOFF + olo) * slo + lds32(bufg + CWOFF + ohi) * shi;
 #else
         const int mlo = sign_mask<0x9999>(wd[i]), mhi = sign_mask<0xBBBB>(wd[i]);  // 0 / -1 from bit 15 / bit 31
         p0 += ((lds32(bufg + olo) ^ mlo) - mlo) + ((lds32(bufg + ohi) ^ mhi) - mhi);
-        p1 += ((lds32(bufg + CWOFF + olo) ^ mlo) - mlo) + ((lds32(bufg + CWOFF + ohi) ^ mhi) - mhi);
+        if (NC == 2) p1 += ((lds32(bufg + CWOFF + olo) ^ mlo) - mlo) + ((lds32(bufg + CWOFF + ohi) ^ mhi) - mhi);
 #endif
     }
 }
@@ -203,6 +204,7 @@ __device__ __forceinline__ void gather_preload(const uint16_t *__restrict__ fwd2
 
 // operator thread `ot` adds the 8 sections of group g into its rows k = ot + 256 j of both codewords; the table
 // words of batch b+1 are in flight while batch b is gathered
+template <int NC>
 __device__ __forceinline__ void gather_group2(const uint16_t *__restrict__ fwd2, int g, int n, int ot, const char *bufg,
                                               long long (&acc)[NR][2], const uint4 (&w0)[KB]) {
     const uint4 *tab = reinterpret_cast<const uint4 *>(fwd2) + (size_t)g * n + ot;
@@ -231,9 +233,9 @@ __device__ __forceinline__ void gather_group2(const uint16_t *__restrict__ fwd2,
 #pragma unroll
         for (int j = 0; j < KB; j++) {
             int p0 = 0, p1 = 0;  // 8 terms of < 2^27 each
-            gather8(w[b & 1][j], bufg, p0, p1);
+            gather8<NC>(w[b & 1][j], bufg, p0, p1);
             acc[b * KB + j][0] += p0;
-            acc[b * KB + j][1] += p1;
+            if (NC == 2) acc[b * KB + j][1] += p1;
         }
     }
 }
@@ -298,6 +300,31 @@ __device__ __forceinline__ void transform_unit(const Args &a, const Slot *sl, in
     const double fs = sl->fscale;
 #pragma unroll
     for (int e = 0; e < 16; e++) st[e * 32 + q] = __double2int_rn(x[e] * fs);  // word e*32+q = fq_word(lo)
+}
+
+// Operator warps, one pass over the sections: fold group i+1 and gather group i-1 while the transform warps work on
+// group i (same barrier sequence as the transform warps' loop in role_main).  NC = 2: both slots, planes at z0 /
+// z0 + ZPLANE and buf / buf + CWOFF; NC = 1: one slot, z0 and buf point at its planes, sums in acc[.][0].
+template <int NC>
+__device__ __forceinline__ void ow_pass(const Args &a, int n, int G, int rt, int rw, int q, const char *z0, char *buf,
+                                        bool anyfold, long long (&acc)[NR][2]) {
+    uint4 pre[KB];  // first table words of the next gather
+#pragma unroll
+    for (int j = 0; j < NR; j++) acc[j][0] = acc[j][1] = 0;
+    if (anyfold) fold_section2<NC>(a.inv2, rw, q, z0, buf + rw * SLOT);
+    if (P2_PRELOAD) gather_preload(a.fwd2, 0, n, rt, pre);
+    bar_all();
+    for (int i = 0;; i++) {  // (one copy of the gather code: the last trip gathers group G-1 and leaves)
+        if (i >= 1) {
+            if (!P2_PRELOAD) gather_preload(a.fwd2, i - 1, n, rt, pre);
+            gather_group2<NC>(a.fwd2, i - 1, n, rt, buf + ((i - 1) & 1) * BUF, acc, pre);
+        }
+        if (i == G) break;
+        bar_ow();  // every operator warp has finished reading that buffer before group i+1 is folded into it
+        if (i + 1 < G && anyfold) fold_section2<NC>(a.inv2, (i + 1) * S + rw, q, z0, buf + ((i + 1) & 1) * BUF + rw * SLOT);
+        if (P2_PRELOAD && i >= 1) gather_preload(a.fwd2, i, n, rt, pre);
+        bar_all();
+    }
 }
 
 template <bool OW>
@@ -425,24 +452,24 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
 
         // ---------------- one pass over the sections, software-pipelined by role
         double sq0 = 0.0, sq1 = 0.0, gmax0 = -INFINITY, gmax1 = -INFINITY, lmin0 = INFINITY, lmin1 = INFINITY;
-        uint4 pre[KB];  // operator warps: first table words of the next gather
-        if constexpr (OW) {
-#pragma unroll
-            for (int j = 0; j < NR; j++) acc[j][0] = acc[j][1] = 0;
-            if (anyfold) fold_section2(a.inv2, rw, q, zq, buf + rw * SLOT);
-            if (P2_PRELOAD) gather_preload(a.fwd2, 0, n, rt, pre);
+        const bool both = (m0 >= 0) && (m1 >= 0);
+#ifdef P2_TRACE
+        int trow = -1;
+        if (tid == 0) {
+            trow = atomicAdd(&g_trace_n, 1);
+            if (trow < TRACE_MAX) {
+                g_trace[trow * 4 + 0] = gtime();
+                g_trace[trow * 4 + 3] = ((unsigned long long)blockIdx.x << 32) | ((unsigned)(m0 + 1) << 28) | ((unsigned)(m1 + 1) << 24) |
+                                        ((unsigned)(m0 >= 0 ? slot[0].t : 0) << 8) | (unsigned)(m1 >= 0 ? slot[1].t : 0);
+            }
         }
-        bar_all();
-        for (int i = 0; i < G; i++) {
-            if constexpr (OW) {
-                if (i >= 1) {
-                    if (!P2_PRELOAD) gather_preload(a.fwd2, i - 1, n, rt, pre);
-                    gather_group2(a.fwd2, i - 1, n, rt, buf + ((i - 1) & 1) * BUF, acc, pre);
-                }
-                bar_ow();  // every operator warp has finished reading that buffer before group i+1 is folded into it
-                if (i + 1 < G && anyfold) fold_section2(a.inv2, (i + 1) * S + rw, q, zq, buf + ((i + 1) & 1) * BUF + rw * SLOT);
-                if (P2_PRELOAD && i >= 1) gather_preload(a.fwd2, i, n, rt, pre);
-            } else {
+#endif
+        if constexpr (OW) {
+            if (both) ow_pass<2>(a, n, G, rt, rw, q, zq, buf, anyfold, acc);
+            else ow_pass<1>(a, n, G, rt, rw, q, zq + (m0 >= 0 ? 0 : ZPLANE), buf + (m0 >= 0 ? 0 : CWOFF), anyfold, acc);
+        } else {
+            bar_all();
+            for (int i = 0; i < G; i++) {
                 char *sec = buf + (i & 1) * BUF + rw * SLOT;
                 int *Sp = reinterpret_cast<int *>(scr + rw * SCR), *Sn = Sp + SCR / 8;
                 if (P2_PREFETCH_BETA && i + 1 < G) {  // beta of the next group: HBM -> L2 while this group is transformed
@@ -450,19 +477,22 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
                     if (m0 == 0 && !slot[0].first_zero) prefetch_l2(a.beta + (size_t)slot[0].b * L * M + nxt);
                     if (m1 == 0 && !slot[1].first_zero) prefetch_l2(a.beta + (size_t)slot[1].b * L * M + nxt);
                 }
-                if (m0 >= 0)
-                    transform_unit(a, slot, i * S + rw, q, reinterpret_cast<int *>(sec), Sp, Sn, rtp, inv_rt_n, sq0, gmax0, lmin0);
-                if (m1 >= 0)
-                    transform_unit(a, slot + 1, i * S + rw, q, reinterpret_cast<int *>(sec + CWOFF), Sp, Sn, rtp, inv_rt_n, sq1,
-                                   gmax1, lmin1);
+#pragma unroll TW_UNROLL
+                for (int c = 0; c < 2; c++) {  // (one copy of the transform code: instruction-cache footprint)
+                    if ((c ? m1 : m0) < 0) continue;
+                    double dsq = 0.0, dmax = -INFINITY, dmin = INFINITY;
+                    transform_unit(a, slot + c, i * S + rw, q, reinterpret_cast<int *>(sec + c * CWOFF), Sp, Sn, rtp, inv_rt_n, dsq,
+                                   dmax, dmin);
+                    if (c) { sq1 += dsq; gmax1 = fmax(gmax1, dmax); lmin1 = fmin(lmin1, dmin); }
+                    else { sq0 += dsq; gmax0 = fmax(gmax0, dmax); lmin0 = fmin(lmin0, dmin); }
+                }
+                bar_all();
             }
-            bar_all();
-        }
-        if constexpr (OW) {
-            if (!P2_PRELOAD) gather_preload(a.fwd2, G - 1, n, rt, pre);
-            gather_group2(a.fwd2, G - 1, n, rt, buf + ((G - 1) & 1) * BUF, acc, pre);
         }
 
+#ifdef P2_TRACE
+        if (tid == 0 && trow >= 0 && trow < TRACE_MAX) g_trace[trow * 4 + 1] = gtime();
+#endif
         // ---------------- end of pass: Onsager term and residual (sparc_ldpc.py:220), or z = y - A beta0 (:197-198)
 #pragma unroll
         for (int c = 0; c < 2; c++) {
@@ -477,7 +507,7 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
 #pragma unroll
                     for (int j = 0; j < NR; j++) {
                         const int k = rt + NOW * j;
-                        if (k < n) zc[k] = y[k] - ((double)acc[j][c] * funit) / rt_n;
+                        if (k < n) zc[k] = y[k] - ((double)((both && c) ? acc[j][1] : acc[j][0]) * funit) / rt_n;
                     }
                 }
                 bar_all();
@@ -495,7 +525,7 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
 #pragma unroll
                     for (int j = 0; j < NR; j++) {
                         const int k = rt + NOW * j;
-                        if (k < n) zc[k] = (y[k] - ((double)acc[j][c] * funit) / rt_n) + (zc[k] / tau2) * ons;
+                        if (k < n) zc[k] = (y[k] - ((double)((both && c) ? acc[j][1] : acc[j][0]) * funit) / rt_n) + (zc[k] / tau2) * ons;
                     }
                 }
                 bar_all();
@@ -509,6 +539,9 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
             }
         }
         bar_all();
+#ifdef P2_TRACE
+        if (tid == 0 && trow >= 0 && trow < TRACE_MAX) g_trace[trow * 4 + 2] = gtime();
+#endif
     }
 }
 
@@ -540,6 +573,10 @@ __global__ void __launch_bounds__(512, 1) amp2_kernel(Args a) {
     // |F| <= sqrt(n P_l) <= cmax; the 1e-6 margin keeps |F_q| strictly below 2^27 (sums of 8 terms stay in int32)
     const double fscale_q = scalbn(1.0, 27 - ceil_exp(cmax * (1.0 + 1e-6)));
     bar_all();
+#ifdef P2_DESYNC  // experiment: start the CTAs out of phase
+    for (int i = 0; i < (int)(blockIdx.x % 37); i++) __nanosleep(20000);
+    __syncthreads();
+#endif
     if (tid < NOW) {
 #if P2_REGS_TW
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(256 - P2_REGS_TW));
@@ -554,6 +591,20 @@ __global__ void __launch_bounds__(512, 1) amp2_kernel(Args a) {
 }
 
 }  // namespace p2
+
+#ifdef P2_TRACE
+extern "C" int sb_p2_trace_read(unsigned long long *out, int max_rows) {
+    int n = 0;
+    SB_CUDA(cudaDeviceSynchronize());
+    SB_CUDA(cudaMemcpyFromSymbol(&n, p2::g_trace_n, sizeof(int)));
+    if (n > p2::TRACE_MAX) n = p2::TRACE_MAX;
+    if (n > max_rows) n = max_rows;
+    SB_CUDA(cudaMemcpyFromSymbol(out, p2::g_trace, sizeof(unsigned long long) * 4 * (size_t)n));
+    const int zero = 0;
+    SB_CUDA(cudaMemcpyToSymbol(p2::g_trace_n, &zero, sizeof(int)));
+    return n;
+}
+#endif
 
 // FAST mode, all sections active, pair tables present.  scratch: [2][B][n] doubles (sb_amp_batch): the first
 // 2 * grid * n hold z of the resident slots, the work counter sits behind them when B > grid.
