@@ -204,13 +204,18 @@ int sb_dense_amp_batch_sharded(sb_dense *d, const double *y, const double *Pl_lo
  * area; the last CTA publishes the epoch in every peer's flag word (system-scope release); the residual kernel adds
  * the slots in rank order after all local flags have arrived, so z stays bit-identical on every rank.
  * slots[r] / flags[r]: rank r's area / flag words AS MAPPED IN THIS PROCESS (r = rank: the local ones).
- * *epoch_io: exchange counter, 0 before the first call, carried from call to call (all ranks make the same calls).
+ * *epoch_io: exchange counter, 0 before the first call, carried from call to call (all ranks make the same calls);
+ *            written back on EVERY return path.  After a failed call (SB_ECUDA: a peer did not arrive) the exchange
+ *            is out of step with its peers: free and re-allocate the areas collectively before using it again.
  * timeout_ms: a peer that does not arrive in time makes the call fail with SB_ECUDA instead of hanging. */
 #define SB_P2P_MAX 8
 typedef struct {
     int rank, world, timeout_ms;
     double *slots[SB_P2P_MAX];
     unsigned long long *flags[SB_P2P_MAX];
+    long slot_doubles; /* doubles per slot the areas were ALLOCATED for (area = 2 * world * slot_doubles): the slot and
+                          parity strides, fixed for the life of the exchange, so that calls with different B never
+                          overlap an area a slower peer may still be reading; every call needs B*n + B <= slot_doubles */
 } sb_p2p;
 int sb_enable_peer_access(int peer_device); /* cudaDeviceEnablePeerAccess from the current device */
 /* receive areas shared between processes: cudaMalloc + cudaIpcGetMemHandle on the owner (zero-initialised),

@@ -103,17 +103,69 @@ def calc_E_batch(X, I_a, snr_dB, sparcparams, threshold=0.5, rng=None):
     return Eo, st
 
 
+def _full(a):
+    """An array printed in full, as the reference's np.set_printoptions(threshold=nan) intends (amp_exit.py:261)."""
+    import sys
+    return np.array2string(np.asarray(a), threshold=sys.maxsize)
+
+
+def _export_row(csv_filename, I_a, snr_dB, X, E_host):
+    """One (header, row) pair appended per sample, exactly the reference's layout (amp_exit.py:262-268)."""
+    import csv
+    with open(csv_filename, "a") as fh:
+        w = csv.DictWriter(fh, fieldnames=["I_a", "snr_dB", "X", "E"])
+        w.writeheader()
+        w.writerow({"I_a": I_a, "snr_dB": snr_dB, "X": _full(X), "E": _full(E_host)})
+
+
 def calc_E(X, I_a, snr_dB, sparcparams, csv_filename=None, threshold=0.5):
     """Extrinsic LLRs of one EXIT sample (amp_exit.py:185-270)."""
     Eo, _ = calc_E_batch(np.asarray(X).reshape(1, -1), I_a, snr_dB, sparcparams, threshold)
     E_host = Eo.cpu().numpy().reshape(-1)
     if csv_filename is not None:
-        import csv
-        with open(csv_filename, "a") as fh:
-            w = csv.DictWriter(fh, fieldnames=["I_a", "snr_dB", "X", "E"])   # :265
-            w.writeheader()
-            w.writerow({"I_a": I_a, "snr_dB": snr_dB, "X": X, "E": E_host})
+        _export_row(csv_filename, I_a, snr_dB, X, E_host)
     return E_host
+
+
+class imported_E:
+    """E of one sample read back from a CSV export (amp_exit.py:14-25)."""
+
+    def __init__(self, X, E, I_a, SNR_dB):
+        self.X, self.E, self.I_a, self.SNR_dB = X, E, I_a, SNR_dB
+
+    def __eq__(self, other):
+        return (self.X == other.X).all() and (self.E == other.E).all() and self.I_a == other.I_a and self.SNR_dB == other.SNR_dB
+
+
+def import_E_fromfile(fileName, datapoints, repeats, Llogm):
+    """Reads the (header, row) pairs calc_E(csv_filename=...) appended (amp_exit.py:353-398) into a dictionary keyed
+    'round(I_a, 1) round(snr_dB) l' with l the first repetition index still free -- the reference's keys, including
+    their rounding (ten I_a values per curve are assumed, :374)."""
+    import csv
+    import re
+    rx = re.compile(r"[-+]? (?: (?: \d* \. \d+ ) | (?: \d+ \.? ) )(?: [Ee] [+-]? \d+ ) ?", re.VERBOSE)
+    out = {}
+    with open(fileName) as fh:
+        for _i in range(repeats):
+            for _k in range(10):
+                for _j in range(datapoints):
+                    row = next(csv.DictReader(fh), None)          # a fresh reader per sample: header, then one row
+                    if row is None:
+                        return out
+                    Ev = np.asarray(rx.findall(row["E"]), dtype=np.float64)
+                    Xv = np.asarray(rx.findall(row["X"]), dtype=np.float64).astype(np.int64)
+                    I_a, snr = float(row["I_a"]), float(row["snr_dB"])
+                    item = imported_E(X=Xv, E=Ev, I_a=I_a, SNR_dB=snr)
+                    for l in range(repeats):
+                        key = str(np.round(I_a, 1)) + " " + str(int(np.round(snr))) + " " + str(int(l))
+                        if key in out:
+                            if out[key] == item:
+                                print("repeat dict")
+                                break
+                            continue
+                        out[key] = item
+                        break
+    return out
 
 
 def _density(counts, edges):
@@ -172,11 +224,9 @@ def amp_exit_curve(sparcparams, low_snr_dB, high_snr_dB, repeats, x_axis_points,
                    chunk=None, rng=None, group=None):
     """AMP EXIT curves at 4 SNRs (amp_exit.py:520-631).  Samples are generated in the reference's nested order
     (repeat, snr, I_a), decoded in device batches, and I_e is computed per sample and averaged over repeats.
-    With `group` (a torch.distributed process group) sample g is decoded by rank g mod world and the I_e
-    sums are all-reduced.  Returns (I_a_range, I_e [4, x_axis_points], poly_coeff)."""
-    if import_data:
-        raise NotImplementedError("import of exported E data (amp_exit.py:353-398) is host-side CSV parsing; "
-                                  "re-run with import_data=False")
+    With `group` (a torch.distributed process group, or True for the world group) sample g is decoded by rank
+    g mod world and the per-sample I_e values are exchanged (a sum over disjoint supports), then averaged in the
+    reference's order: the curve is bit-identical to the one-rank run on every rank.  Returns (I_a_range, I_e [4, x_axis_points], poly_coeff)."""
     t0 = time.time()
     rng = S._rng(rng)
     L, M = sparcparams.L, sparcparams.M
@@ -184,13 +234,33 @@ def amp_exit_curve(sparcparams, low_snr_dB, high_snr_dB, repeats, x_axis_points,
     curves = 4
     I_a_range = np.linspace(0, 0.99, x_axis_points)
     snr_dB = np.linspace(low_snr_dB, high_snr_dB, curves)
+    if import_data:   # E was exported by an earlier run: only histograms and I_e are computed (amp_exit.py:550-555,:575-583)
+        if import_csv_filename is None:
+            print("Please enter a valid csv filename in import_csv_filename")
+        d = import_E_fromfile(import_csv_filename, curves, repeats, nbits)
+        print(len(d))
+        acc = np.zeros((curves, x_axis_points))
+        for k in range(repeats):
+            items = [d[str(np.round(I_a, 1)) + " " + str(int(np.round(s_dB))) + " " + str(k)]
+                     for s_dB in snr_dB for I_a in I_a_range]
+            for a in items:
+                assert len(a.X) == nbits and len(a.E) == nbits
+            Xm = np.stack([a.X for a in items])
+            Ed = torch.from_numpy(np.stack([a.E for a in items])).to(E._dev())
+            pos, neg, bw = hist_E_batch(Xm, Ed, bin_number, 60, -60)
+            for q in range(len(items)):
+                acc[q // x_axis_points, q % x_axis_points] += calc_I_e(pos[q], neg[q], bw)
+        I_e = acc / repeats
+        poly_coeff = polynomial(I_a_range, I_e[poly_curve, :])
+        print("The coefficients for the polynomial are: ", poly_coeff)
+        print("Wall clock time elapsed: ", time.time() - t0)
+        return I_a_range, I_e, poly_coeff
     triples = [(k, j, i) for k in range(repeats) for j in range(curves) for i in range(x_axis_points)]
     chunk = chunk or min(len(triples), 512)
-    rank, world = 0, 1
-    if group is not None:
-        import torch.distributed as dist
-        rank, world = dist.get_rank(group), dist.get_world_size(group)
-    acc = np.zeros((curves, x_axis_points))
+    from . import dist as SD
+    rank, world = SD.group_info(group)
+    pg = None if group is True else group
+    ie = np.zeros((repeats, curves, x_axis_points))      # I_e of every sample; each entry is written by ONE rank
     for c0 in range(0, len(triples), chunk):
         part = triples[c0:c0 + chunk]
         # every rank consumes the whole host stream so that sample g is the same codeword everywhere
@@ -216,16 +286,24 @@ def amp_exit_curve(sparcparams, low_snr_dB, high_snr_dB, repeats, x_axis_points,
             rep = _Replay([states[q] for q in mine])
             Xm = np.stack([Xs[q] for q in mine])
             Eo = _calc_E_replay(Xm, [Ias[q] for q in mine], [snrs[q] for q in mine], sparcparams, threshold, rep)
+            if export_csv_filename is not None:                                 # :262-268, rows of this rank
+                Eh = Eo.cpu().numpy()
+                fn = export_csv_filename if world == 1 else "%s.rank%d" % (export_csv_filename, rank)  # one file per rank
+                for m_, q in enumerate(mine):
+                    _export_row(fn, Ias[q], snrs[q], Xm[m_], Eh[m_])
             pos, neg, bw = hist_E_batch(Xm, Eo, bin_number, 60, -60)           # :587
             for m_, q in enumerate(mine):
                 k, j, i = part[q]
-                acc[j, i] += calc_I_e(pos[m_], neg[m_], bw)                      # :590-592
+                ie[k, j, i] = calc_I_e(pos[m_], neg[m_], bw)                     # :590
         rng.set_state(end_state)
-    if group is not None:
+    if world > 1:   # disjoint supports: the sum is an exact all-gather (x + 0.0 == x), NCCL over NVLink on GPUs
         import torch.distributed as dist
-        t = torch.from_numpy(acc).to(E._dev() if dist.get_backend(group) == "nccl" else "cpu")
-        dist.all_reduce(t, group=group)
-        acc = t.cpu().numpy()
+        t = torch.from_numpy(ie).to(E._dev() if dist.get_backend(pg) == "nccl" else "cpu")
+        dist.all_reduce(t, group=pg)
+        ie = t.cpu().numpy()
+    acc = np.zeros((curves, x_axis_points))
+    for k in range(repeats):                                                     # the reference's order of additions (:592)
+        acc = acc + ie[k]
     I_e = acc / repeats                                                          # :595
     poly_coeff = polynomial(I_a_range, I_e[poly_curve, :])                       # :597
     print("The coefficients for the polynomial are: ", poly_coeff)

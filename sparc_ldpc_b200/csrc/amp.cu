@@ -167,7 +167,7 @@ static void build_fast_tables(const uint32_t *ordering, int L, int M, int n, int
     // selects the latter for experiments when two CTAs fit.
     if (logM > 9) return;
     ft.PW = 16;
-    if (const char *env = getenv("SB_AMP_POOL"))
+    if (const char *env = knob("SB_AMP_POOL"))
         if (atoi(env) == 8 && TEAM == 32 && 2 * (fast_smem_bytes(logM, n, 8) + 1024) <= 227 * 1024) ft.PW = 8;
     const int PW = ft.PW;
     ft.GQ = L / PW;

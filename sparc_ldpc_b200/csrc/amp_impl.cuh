@@ -937,7 +937,7 @@ static int pick_threads(int n, int L, int pw, size_t *smem_out, int *W_out, int 
     // M = 1024, which has no scheduled gather table, whenever two CTAs fit)
     if (QUANT && TEAM == 32 && (pw == 8 || (LOGM > 9 && 2 * (Smem<LOGM, QUANT>::bytes(n, 256 / TEAM) + 1024) <= 227 * 1024)))
         nt = 256;
-    const char *env = getenv("SB_AMP_THREADS");
+    const char *env = knob("SB_AMP_THREADS");
     if (env) nt = atoi(env);
     if (nt > 512) nt = 512;
     nt = (nt / 32) * 32;

@@ -273,7 +273,7 @@ extern "C" int sb_bp_batch(const sb_graph *g, int rule, const double *ch, int B,
     cudaStream_t st = (cudaStream_t)stream;
     // local-array variant (no shared-memory scratch): one thread per check, up to 768; SB_BP_SCRATCH=1 forces the scratch variant
     const size_t msgb = sizeof(double) * (size_t)g->Nmsg;
-    const bool reg_ok = rule != SB_BP_SUMPROD && g->dcmax <= 24 && msgb <= 227 * 1024 && !getenv("SB_BP_SCRATCH");
+    const bool reg_ok = rule != SB_BP_SUMPROD && g->dcmax <= 24 && msgb <= 227 * 1024 && !knob("SB_BP_SCRATCH");
     if (rule == SB_BP_SUMPROD2_FAST && !reg_ok) rule = SB_BP_SUMPROD2;  // the scratch-column kernel has no FAST variant
     if (reg_ok) {
         int ntr = ((g->Nc + 31) / 32) * 32;

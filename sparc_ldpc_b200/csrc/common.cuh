@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/sparc_b200.h"
@@ -33,6 +34,18 @@ inline int fail(int code, const char *fmt, const char *a = "", long b = 0) {
         sb::g_launches.fetch_add(1);                    \
         SB_CUDA(cudaGetLastError());                    \
     } while (0)
+
+// Tuning knobs read from the environment exist only in experiment builds (make EXTRA=-DSB_EXPERIMENT,
+// tools/ab_build*.sh): a release build ignores them, so a stray variable cannot change the grid or the
+// shared-memory size of a kernel.
+inline const char *knob(const char *name) {
+#ifdef SB_EXPERIMENT
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
 
 inline int ilog2(int v) {
     int r = 0;

@@ -599,7 +599,7 @@ static void plan_slices(const sb_dense *d, int Mrows, int K, int B, int BN, int 
     if (s > 64) s = 64;
     if (s > nkb) s = nkb;
     int per = (nkb + s - 1) / s;
-    const char *env = getenv("SB_DENSE_CHUNK_KB");
+    const char *env = knob("SB_DENSE_CHUNK_KB");
     const int chunk = env ? atoi(env) : 32;
     if (per > chunk) per = ((per + chunk - 1) / chunk) * chunk;  // whole chunks per slice
     *kb_per_slice = per;
@@ -607,7 +607,7 @@ static void plan_slices(const sb_dense *d, int Mrows, int K, int B, int BN, int 
 }
 
 static int pick_bn(int B) {
-    const char *env = getenv("SB_DENSE_BN");
+    const char *env = knob("SB_DENSE_BN");
     if (env) return atoi(env) == 256 ? 256 : 128;
     return B > 128 ? 256 : 128;
 }
@@ -667,7 +667,7 @@ static int dense_gemm_launch(const sb_dense *d, int transpose, const __nv_bfloat
     const int BN = pick_bn(B);
     const int mtiles = (Mrows + GM - 1) / GM;
     int CL = 2;  // cluster size: the codeword-side tile is fetched once per cluster (SB_DENSE_CLUSTER = 1 | 2 | 4)
-    if (const char *env = getenv("SB_DENSE_CLUSTER")) CL = atoi(env);
+    if (const char *env = knob("SB_DENSE_CLUSTER")) CL = atoi(env);
     if (CL != 1 && CL != 2 && CL != 4) CL = 2;
     while (CL > 1 && mtiles < CL) CL /= 2;
     CUtensorMap mapB;
@@ -676,7 +676,7 @@ static int dense_gemm_launch(const sb_dense *d, int transpose, const __nv_bfloat
     int slices, per;
     plan_slices(d, Mrows, K, B, BN, &slices, &per);
     const int nkb = (K + GK - 1) / GK;
-    const char *env = getenv("SB_DENSE_CHUNK_KB");
+    const char *env = knob("SB_DENSE_CHUNK_KB");
     const int chunk = env ? atoi(env) : 32;
     const long sstride = (long)B * Mrows;
     // row tiles padded to whole clusters: the extra CTAs read zeros (TMA out-of-range fill) and store nothing
@@ -783,9 +783,17 @@ static int dense_amp_impl(sb_dense *d, const double *y, const double *Pl, double
     int slices = 0; long ss = 0;
     // after a GEMM of partial A beta: (sharded) fold the K slices into xbuf, append |beta|^2, sum over the ranks
     // peer-memory exchange state (px != NULL): S doubles per slot, areas alternate with the epoch's parity
-    const long S = (long)B * n + B;
+    // (the slot / parity strides are the ALLOCATED slot size, not this call's B*n + B: a call with a smaller batch
+    // must not put its parity-1 area over memory that a slower peer may still be reading from the previous call)
+    const long S = px ? px->slot_doubles : (long)B * n + B;
+    if (px && (px->slot_doubles < (long)B * n + B || px->world < 1 || px->world > SB_P2P_MAX))
+        return fail(SB_EINVAL, "sb_dense_amp_batch_p2p: the peer areas hold %s%ld doubles per slot, fewer than B*n + B", "", px->slot_doubles);
     P2pDev pd;
     unsigned long long epoch = epoch_io ? *epoch_io : 0;
+    struct EpochGuard {  // the host counter follows the flags already published, on every exit path
+        unsigned long long *io, *cur;
+        ~EpochGuard() { if (io) *io = *cur; }
+    } epoch_guard{epoch_io, &epoch};
     const double *p2p_area = nullptr;
     if (px) {
         for (int r = 0; r < px->world; r++) { pd.slots[r] = px->slots[r]; pd.flags[r] = px->flags[r]; }
@@ -872,7 +880,6 @@ static int dense_amp_impl(sb_dense *d, const double *y, const double *Pl, double
         }
     }
     if (px) {
-        if (epoch_io) *epoch_io = epoch;
         int perr = 0;
         SB_CUDA(cudaMemcpyAsync(&perr, d->p2p_done + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         SB_CUDA(cudaStreamSynchronize(st));

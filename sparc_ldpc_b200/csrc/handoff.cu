@@ -449,9 +449,10 @@ extern "C" int sb_sp2bp_llr_batch(const double *beta, long beta_stride, int beta
     if ((sections == nullptr) != (nsec == nullptr)) return fail(SB_EINVAL, "sb_sp2bp_llr_batch: sections and nsec go together%s", "");
     const int maxcount = sections ? L_stride : count;
     if (B == 0 || maxcount <= 0) return SB_OK;
-    if (M >= 64 && !getenv("SB_HANDOFF_V1")) {  // 16 sections per CTA, one lane per (section, bit) chain
+    if (M >= 64 && !knob("SB_HANDOFF_V1")) {  // 16 sections per CTA, one lane per (section, bit) chain
         const int logM = ilog2(M);
-        const int R = getenv("SB_SP2BP_R") ? atoi(getenv("SB_SP2BP_R")) : 8;  // 8 measured best (1.26 ms vs 1.54 at 16, 1.38 at 4; 2.03 one warp per section)
+        int R = knob("SB_SP2BP_R") ? atoi(knob("SB_SP2BP_R")) : 8;
+        if (R != 4 && R != 8 && R != 16) R = 8;  // only these are instantiated  // 8 measured best (1.26 ms vs 1.54 at 16, 1.38 at 4; 2.03 one warp per section)
         dim3 grid16((maxcount + R - 1) / R, B);
         const size_t smem16 = sizeof(double) * R * (size_t)(M + 1);
         if (R == 4) {
@@ -500,7 +501,7 @@ extern "C" int sb_bp2sp_prior_batch(const double *app, int ls, const double *bet
     const size_t smem = sizeof(double) * (size_t)wpb * (M + 16);
     if (smem > 48 * 1024)
         SB_CUDA(cudaFuncSetAttribute(bp2sp_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (M == 512 && !getenv("SB_HANDOFF_V1")) {
+    if (M == 512 && !knob("SB_HANDOFF_V1")) {
         SB_CUDA(cudaFuncSetAttribute(bp2sp_prior_kernel512, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         bp2sp_prior_kernel512<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(app, ls, beta_prev, L, n, Pl, scale_by_power,
                                                                              input_is_prob, beta_init);

@@ -47,6 +47,7 @@ class Stages:
     def __init__(self):
         self.amp_idx, self.ldpc_idx = [], []      # decisions after each AMP / LDPC round
         self.amp_exec, self.bp_it = [], []        # executed AMP iterations [B] / BP iterations [B] per call
+        self.amp_flags = []                       # SB_AMP_* status bits [B] per AMP call
         self.amp_sections = []                    # sections processed per AMP call ([B] tensor or int)
         self.extra = {}
 
@@ -59,10 +60,20 @@ class Stages:
             return errs / total_bits
         return rows(self.amp_idx), rows(self.ldpc_idx)
 
+    def ref_nan_count(self):
+        """Codewords on which the reference's own global-max softmax would have left fp64's normal range in some
+        AMP call (SB_AMP_REF_NAN): the kernel computes them accurately, the reference would not."""
+        from ._lib import SB_AMP_REF_NAN
+        if not self.amp_flags:
+            return torch.zeros((), dtype=torch.int64)
+        f = torch.stack([(x & SB_AMP_REF_NAN) != 0 for x in self.amp_flags]).any(dim=0)
+        return f.sum()   # 0-dim device tensor: no host synchronisation here
+
 
 def _amp(su, st, y, beta0=None, sections=None, nsec=None, Pl=None):
     res = su.op.amp(y, su.Pl_dev if Pl is None else Pl, su.T, beta0=beta0, sections=sections, nsec=nsec)
     st.amp_exec.append(res.n_exec)
+    st.amp_flags.append(res.flags)   # SB_AMP_STOPPED / SB_AMP_REF_NAN per codeword (include/sparc_b200.h)
     st.amp_sections.append(su.L if nsec is None else nsec)
     return res
 

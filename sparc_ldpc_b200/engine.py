@@ -165,6 +165,22 @@ class Operator:
         return AmpResult(beta, iters, n_exec, flags, tau2)
 
 
+def section_softmax(s, Pl, tau2, L, M, n):
+    """Denoiser of amp() alone (sparc_ldpc.py:214-219) for a batch: s [B, L*M] = beta + A^T z, tau2 [B] ->
+    (beta [B, L*M], sumsq [B, L]).  For design operators that are not ours (foreign Ab / Az closures)."""
+    _chk(s, F64, "s")
+    _chk(Pl, F64, "Pl")
+    _chk(tau2, F64, "tau2")
+    B = s.shape[0]
+    if s.shape[1] != L * M or Pl.numel() != L or tau2.numel() != B:
+        raise ValueError("s must be [B, L*M], Pl [L], tau2 [B]")
+    beta = torch.empty_like(s)
+    sumsq = torch.empty((B, L), dtype=F64, device=s.device)
+    check(_lib.lib().sb_section_softmax_batch(_p(s), _p(Pl), _p(tau2), 0, int(L), int(M), int(n), B, _p(beta), _p(sumsq),
+                                              _stream()), "sb_section_softmax_batch")
+    return beta, sumsq
+
+
 class DenseOperator:
     """Dense design matrix A [n, L*M] on the device (Gaussian-A mode; the reference's amp() accepts any Ab/Az
     closures, sparc_ldpc.py:189).  A beta and A^T z are libsparc_b200's tcgen05 / TMA GEMMs over the batch with a
@@ -311,7 +327,7 @@ class DenseOperator:
 class _SbP2p(_ct.Structure):
     """struct sb_p2p of include/sparc_b200.h"""
     _fields_ = [("rank", _ct.c_int), ("world", _ct.c_int), ("timeout_ms", _ct.c_int),
-                ("slots", _ct.c_void_p * 8), ("flags", _ct.c_void_p * 8)]
+                ("slots", _ct.c_void_p * 8), ("flags", _ct.c_void_p * 8), ("slot_doubles", _ct.c_long)]
 
 
 class PeerExchange:
@@ -326,6 +342,7 @@ class PeerExchange:
         self._keep = (areas, flagws)          # the mapped tensors must outlive the exchange
         self.cstruct = _SbP2p()
         self.cstruct.rank, self.cstruct.world, self.cstruct.timeout_ms = rank, world, int(timeout_ms)
+        self.cstruct.slot_doubles = int(slot_doubles)
         for r in range(world):
             self.cstruct.slots[r] = areas[r].data_ptr()
             self.cstruct.flags[r] = flagws[r].data_ptr()

@@ -66,21 +66,21 @@ def ber_point(sparcparams, ldpcparams, n_codewords, flow="soft", soft_iter=2, th
                              torch.stack([a.sum() for a in st.amp_exec]).to(torch.int64).sum().reshape(1),
                              (torch.stack([t.sum() for t in st.bp_it]).to(torch.int64).sum().reshape(1)
                               if st.bp_it else torch.zeros(1, dtype=torch.int64, device=su.dev)),
-                             torch.tensor([B], dtype=torch.int64, device=su.dev)])
+                             st.ref_nan_count().to(su.dev).reshape(1), torch.tensor([B], dtype=torch.int64, device=su.dev)])
             totals = row if totals is None else totals + row
             n_amp, n_ldpc = len(st.amp_idx), len(st.ldpc_idx)
     finally:
         E.AMP_MODE = prev_mode
     if totals is None:  # this rank had no codeword: still take part in the reduction
         n_amp, n_ldpc = _stage_counts(flow, soft_iter, su)
-        totals = torch.zeros(2 * (n_amp + n_ldpc) + 3, dtype=torch.int64, device=su.dev)
+        totals = torch.zeros(2 * (n_amp + n_ldpc) + 4, dtype=torch.int64, device=su.dev)
     tot = SD.allreduce_counts(totals, group)
     ns = n_amp + n_ldpc
     n = int(tot[-1])
     bits = n * su.total_bits
     return dict(n_codewords=n, R=su.R, ber_amp=(tot[:n_amp] / bits).tolist(), ber_ldpc=(tot[n_amp:ns] / bits).tolist(),
                 block_errors_amp=tot[ns:ns + n_amp].tolist(), block_errors_ldpc=tot[ns + n_amp:2 * ns].tolist(),
-                amp_iterations=int(tot[2 * ns]), bp_iterations=int(tot[2 * ns + 1]))
+                amp_iterations=int(tot[2 * ns]), bp_iterations=int(tot[2 * ns + 1]), amp_ref_nan=int(tot[2 * ns + 2]))
 
 
 def _stage_counts(flow, soft_iter, su):
@@ -101,12 +101,14 @@ def waterfall_device(sparcparams, ldpcparams, EbN0_dB, n_codewords, R=None, flow
     from .sparc_ldpc import SPARCParams
     sp = sparcparams
     out = []
-    for i, db in enumerate(np.asarray(EbN0_dB, dtype=float)):
+    dbs = np.asarray(EbN0_dB, dtype=float)
+    base_seed = int(kw.pop("seed", 0))          # read ONCE: every point of a sweep derives its stream from it
+    for i, db in enumerate(dbs):
         su = D.make_setup(sp, None if flow == "plain" else ldpcparams)
         Rr = su.R if R is None else R
         sigma = float(np.sqrt(sp.p / (10 ** (db / 20) * 2 * Rr)))
         res = ber_point(SPARCParams(sp.L, sp.M, sigma, sp.p, sp.r, sp.t, sp.a, sp.f, sp.C), ldpcparams, n_codewords,
-                        flow=flow, seed=kw.pop("seed", 0) + i if "seed" in kw else i, **kw)
+                        flow=flow, seed=base_seed * len(dbs) + i, **kw)
         res["EbN0_dB"], res["sigma"] = float(db), sigma
         out.append(res)
     return out

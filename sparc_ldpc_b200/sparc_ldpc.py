@@ -9,11 +9,13 @@ CUDA library these functions raise.
 """
 import csv
 import math
+import os
 
 import numpy as np
 import torch
 
 from . import decoder as D
+from . import dist as SD
 from . import engine as E
 from .ldpc import get_code
 
@@ -136,15 +138,44 @@ def sparc_transforms_gaussian(L, M, n, seed=0, A=None):
 
 def amp(y, sigma_n, Pl, L, M, T, Ab, Az, beta=None):
     """AMP decoder with the reference signature (sparc_ldpc.py:189-222); sigma_n is unused, as there.
-    Ab/Az must be closures returned by sparc_transforms[_shorter] of this module."""
+    With the closures returned by sparc_transforms[_shorter] / sparc_transforms_gaussian of this module the whole
+    loop is one device kernel; with ANY other Ab / Az callables (the reference accepts any, :189) the loop runs
+    here, the two products are the caller's closures and the section softmax is the device kernel
+    sb_section_softmax_batch."""
     return _amp_host(y, Pl, L, M, T, Ab, Az, beta)[0]
+
+
+def _amp_foreign(y, Pl, L, M, T, Ab, Az, beta):
+    """sparc_ldpc.py:189-222 line for line around foreign closures; returns (beta (LM,1), t)."""
+    Pl = np.ascontiguousarray(Pl, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    P, n = np.sum(Pl), y.size                                   # (:190-191)
+    no_init = beta is None or (isinstance(beta, np.ndarray) and beta.dtype == object)
+    if no_init:
+        b, z = np.zeros((L * M, 1)), y                          # (:193-195)
+    else:
+        b = np.asarray(beta, dtype=np.float64).reshape(L * M, 1)
+        z = y - np.asarray(Ab(b), dtype=np.float64).reshape(-1, 1)   # (:197-198)
+    last_tau, t = 0, 0
+    Pld = torch.from_numpy(Pl).cuda()
+    for t in range(T):
+        tau = np.sqrt(np.sum(z ** 2) / n)                       # (:203)
+        if tau == last_tau:                                     # (:204)
+            return b, t
+        last_tau = tau
+        s = b + np.asarray(Az(z), dtype=np.float64).reshape(-1, 1)   # (:213)
+        sd = torch.from_numpy(np.ascontiguousarray(s.reshape(1, -1))).cuda()
+        t2 = torch.tensor([tau ** 2], dtype=F64, device=sd.device)
+        bd, _ = E.section_softmax(sd, Pld, t2, L, M, n)         # (:214-219) on the device
+        b = bd.cpu().numpy().reshape(-1, 1)
+        z = y - np.asarray(Ab(b), dtype=np.float64).reshape(-1, 1) + (z / tau ** 2) * (P - np.sum(b ** 2) / n)   # (:220)
+    return b, t
 
 
 def _amp_host(y, Pl, L, M, T, Ab, Az, beta):
     op = getattr(Ab, "_sb_op", None)
     if op is None or getattr(Az, "_sb_op", None) is not op:
-        raise NotImplementedError("amp() needs the Ab/Az closures returned by sparc_ldpc_b200.sparc_transforms "
-                                  "(foreign operators have no device kernel)")
+        return _amp_foreign(y, Pl, L, M, T, Ab, Az, beta)
     if op.L != L or op.M != M:
         raise AssertionError("operator was built for L=%d, M=%d" % (op.L, op.M))
     no_init = beta is None or (isinstance(beta, np.ndarray) and beta.dtype == object)  # the [None] sentinel (:189)
@@ -230,8 +261,20 @@ def _transmit(su, idx, noise):
     return tx, y
 
 
+def _matrix_seed(seed, rng):
+    """seed=None is the reference's sparc_transforms(seed=None) of the custom-protograph path (sparc_ldpc.py:930-941):
+    a design matrix drawn from OS entropy for EVERY codeword.  Here one matrix serves all codewords of a driver call
+    (the BER is conditioned on that draw instead of averaged over the ensemble -- a documented deviation: tables for
+    one matrix cost ~1 s to build), and its seed is derived from the position of the host RNG stream WITHOUT
+    consuming a draw, so that runs can be replayed and all ranks of a group build the same matrix."""
+    if seed is not None:
+        return seed
+    import zlib
+    return int(zlib.crc32(_rng(rng).get_state()[1].tobytes()) & 0x7FFFFFFF)
+
+
 def _run(flow, sparcparams, ldpcparams, B, rng, seed=0, all_zero=False, **kw):
-    su = D.make_setup(sparcparams, ldpcparams, seed=seed)
+    su = D.make_setup(sparcparams, ldpcparams, seed=_matrix_seed(seed, rng))
     idx, noise = _draw(su, B, sparcparams.sigma, _rng(rng), all_zero)
     tx, y = _transmit(su, idx, noise)
     st = flow(su, y, **kw)
@@ -279,7 +322,7 @@ def hardinitbeta_amp_ldpc_sim(sparcparams, ldpcparams):
 
 def soft_amp_ldpc_hardinit_batch(sparcparams, ldpcparams, soft_iter, threshold, B=1, rng=None):
     ieee = ldpcparams.standard in ("802.11n", "802.16")
-    # custom protographs: all-zero message and a fresh, OS-seeded design matrix per call (sparc_ldpc.py:930-935)
+    # custom protographs: all-zero message and a fresh design matrix per call (sparc_ldpc.py:930-935; _matrix_seed)
     su, st, ba, bl = _run(D.threshold, sparcparams, ldpcparams, B, rng, seed=0 if ieee else None,
                           all_zero=not ieee, soft_iter=soft_iter, thr=threshold)
     return ba, bl, su.R
@@ -307,10 +350,12 @@ def bpsk(x):
 _RATES = ("1/2", "2/3", "3/4", "5/6", "0.45")
 
 
-def sim_ldpc(ldpcparams, sigma, MIN_ERRORS=100, MAX_BLOCKS=400000, chunk=256, rng=None):
+def sim_ldpc(ldpcparams, sigma, MIN_ERRORS=100, MAX_BLOCKS=400000, chunk=256, rng=None, group=None):
     """LDPC + BPSK over AWGN (sparc_ldpc.py:1064-1124), decoded in chunks on the device; the sequential
     stop rule (MIN_ERRORS block errors or MAX_BLOCKS) is replayed on the host and the RNG is rewound to
-    where the reference would have stopped drawing."""
+    where the reference would have stopped drawing.  With `group` (torch.distributed process group, or True for
+    the world group) the blocks of every chunk are decoded by rank j mod world and the error counts exchanged
+    (dist.decode_sharded): same result and RNG state on every rank as the one-rank run."""
     if ldpcparams.r_ldpc not in _RATES:
         raise NameError("Rate unsupported")
     rng = _rng(rng)
@@ -328,8 +373,11 @@ def sim_ldpc(ldpcparams, sigma, MIN_ERRORS=100, MAX_BLOCKS=400000, chunk=256, rn
             xs.append(x)
             ys.append(ch2llr(bpsk(x) + sigma * rng.randn(len(x)), sigma))
         states.append(rng.get_state())
-        app, _ = code.decode_batch(torch.from_numpy(np.asarray(ys)).to(dev))
-        errs = ((app < 0.0).cpu().numpy() != np.asarray(xs).astype(bool)).sum(axis=1)
+        def decode_blocks(blocks):
+            app, _ = code.decode_batch(torch.from_numpy(np.asarray([b[1] for b in blocks])).to(dev))
+            return ((app < 0.0).cpu().numpy() != np.asarray([b[0] for b in blocks]).astype(bool)).sum(axis=1).astype(float).tolist()
+
+        errs = SD.decode_sharded(decode_blocks, list(zip(xs, ys)), group)
         for j in range(nb):
             nbit += int(errs[j])
             nblockerr += 1 if errs[j] else 0
@@ -342,7 +390,16 @@ def sim_ldpc(ldpcparams, sigma, MIN_ERRORS=100, MAX_BLOCKS=400000, chunk=256, rn
 
 
 # ----------------------------------------------------------------------------------- Monte-Carlo drivers
-def _mc(rng, draw_block, decode_blocks, stop_after, MIN_ERRORS, MAX_BLOCKS, chunk):
+def _seqsum(values):
+    """Left-to-right fp64 accumulation, as the reference's `BER = BER + ber` loops (sparc_ldpc.py:1229-1233); the
+    built-in sum() of CPython >= 3.12 adds Python floats with compensation and would round differently."""
+    acc = np.float64(0.0)
+    for v in values:
+        acc = acc + np.float64(v)
+    return acc
+
+
+def _mc(rng, draw_block, decode_blocks, stop_after, MIN_ERRORS, MAX_BLOCKS, chunk, group=None):
     """Sequential stop-rule replay.  draw_block() consumes the RNG for one block and returns
     its inputs; decode_blocks(list) -> per-block result rows; stop_after(row) says whether the block counts
     as an error block.  Returns the rows the reference would have averaged."""
@@ -354,7 +411,7 @@ def _mc(rng, draw_block, decode_blocks, stop_after, MIN_ERRORS, MAX_BLOCKS, chun
             states.append(rng.get_state())
             blocks.append(draw_block())
         states.append(rng.get_state())
-        out = decode_blocks(blocks)
+        out = SD.decode_sharded(decode_blocks, blocks, group)   # (group=None: decode_blocks(blocks))
         for j in range(nb):
             rows.append(out[j])
             nerr += 1 if stop_after(out[j]) else 0
@@ -365,10 +422,10 @@ def _mc(rng, draw_block, decode_blocks, stop_after, MIN_ERRORS, MAX_BLOCKS, chun
 
 
 def _pair_driver(coded_flow, sp_coded, lp, sp_plain, rng, MIN_ERRORS, MAX_BLOCKS, chunk, seed=0, all_zero=False,
-                 **kw):
+                 group=None, **kw):
     """Blocks of (coded simulation, plain simulation at the same overall rate) as in waterfall() and
     soft_hardinit_plot(): per block the coded draw comes first (sparc_ldpc.py:1218-1231)."""
-    su_c = D.make_setup(sp_coded, lp, seed=seed)
+    su_c = D.make_setup(sp_coded, lp, seed=_matrix_seed(seed, rng))
     su_p = D.make_setup(sp_plain, None)
 
     def draw_block():
@@ -386,7 +443,7 @@ def _pair_driver(coded_flow, sp_coded, lp, sp_plain, rng, MIN_ERRORS, MAX_BLOCKS
         bp_, _ = D.plain(su_p, yp).ber(txp, su_p.total_bits)
         return [(ba[j], bl[j], bp_[j, 0]) for j in range(len(blocks))]
 
-    return _mc(rng, draw_block, decode_blocks, lambda row: row[2] != 0, MIN_ERRORS, MAX_BLOCKS, chunk)
+    return _mc(rng, draw_block, decode_blocks, lambda row: row[2] != 0, MIN_ERRORS, MAX_BLOCKS, chunk, group)
 
 
 def _maybe_plot(fn):
@@ -399,10 +456,12 @@ def _maybe_plot(fn):
 
 
 def waterfall(sparcparams, ldpcparams, csv_filename, png_filename, init="soft", pa_param=False, datapoints=10,
-              MIN_ERRORS=100, MAX_BLOCKS=500, bpsk=True, sections=512, chunk=64, EbN0_dB=None, rng=None):
+              MIN_ERRORS=100, MAX_BLOCKS=500, bpsk=True, sections=512, chunk=64, EbN0_dB=None, rng=None, group=None):
     """BER waterfall (sparc_ldpc.py:1126-1282): same grid, sigma convention (20 log10), hard-coded rate 5/6,
     stop rule and CSV schema.  `EbN0_dB` overrides the default linspace(3, 10, datapoints) grid; returns the
-    dict of columns that is written to the CSV."""
+    dict of columns that is written to the CSV.  `group`: decode every chunk's blocks across the ranks of a
+    torch.distributed group (every rank must call with the same arguments and an identically seeded `rng`);
+    columns and final RNG state equal the one-rank run, rank 0 writes the CSV."""
     rng = _rng(rng)
     L, M = sparcparams.L, sparcparams.M
     logm = np.log2(M)
@@ -423,7 +482,7 @@ def waterfall(sparcparams, ldpcparams, csv_filename, png_filename, init="soft", 
     for i, ebno_db in enumerate(grid):
         ebno = 10 ** (ebno_db / 20)
         if bpsk:
-            cols["BER_bpsk"][i] = sim_ldpc(ldpcparams, np.sqrt((1 / ebno) / 2), MIN_ERRORS, MAX_BLOCKS, rng=rng)  # :1189-1193
+            cols["BER_bpsk"][i] = sim_ldpc(ldpcparams, np.sqrt((1 / ebno) / 2), MIN_ERRORS, MAX_BLOCKS, rng=rng, group=group)  # :1189-1193
         snr = ebno / (1 / (2 * R))
         sigma = np.sqrt(p / snr)
         C = 0.5 * np.log2(1 + p / (sigma ** 2))
@@ -431,26 +490,28 @@ def waterfall(sparcparams, ldpcparams, csv_filename, png_filename, init="soft", 
             a = f = r_sparc / C                                        # frozen from the first point (:1202-1204)
         sp_c = SPARCParams(L, M, sigma, p, r_sparc, T, a, f, C)
         sp_p = SPARCParams(L, M, sigma, p, R, T, a, f, C)
-        rows = _pair_driver(flow, sp_c, ldpcparams, sp_p, rng, MIN_ERRORS, MAX_BLOCKS, chunk, **kw)
+        rows = _pair_driver(flow, sp_c, ldpcparams, sp_p, rng, MIN_ERRORS, MAX_BLOCKS, chunk, group=group, **kw)
         nb = len(rows)
         amp = np.array([np.pad(r_[0], (0, max(0, 2 - len(r_[0])))) for r_ in rows])
         ldp = np.array([np.pad(r_[1], (0, max(0, 2 - len(r_[1])))) for r_ in rows])  # hard/originalHard: 0 appended (:1223-1227)
         cols["BER_amp_1"][i], cols["BER_amp_2"][i] = amp[:, 0].sum() / nb, amp[:, 1].sum() / nb
         cols["BER_ldpc"][i], cols["BER_ldpc_2"][i] = ldp[:, 0].sum() / nb, ldp[:, 1].sum() / nb
-        cols["BER_plain"][i] = sum(r_[2] for r_ in rows) / nb
+        cols["BER_plain"][i] = _seqsum(r_[2] for r_ in rows) / nb
     fields = ["EbN0_dB", "BER_amp_1", "BER_ldpc", "BER_amp_2", "BER_ldpc_2", "BER_plain", "BER_bpsk"]  # :1260
-    with open(csv_filename, "a") as fh:
-        w = csv.DictWriter(fh, fieldnames=fields)
-        w.writeheader()
-        for k in range(datapoints):
-            w.writerow(dict(EbN0_dB=grid[k], **{c: cols[c][k] for c in fields[1:]}))
+    if SD.group_info(group)[0] == 0:
+        with open(csv_filename, "a") as fh:
+            w = csv.DictWriter(fh, fieldnames=fields)
+            w.writeheader()
+            for k in range(datapoints):
+                w.writerow(dict(EbN0_dB=grid[k], **{c: cols[c][k] for c in fields[1:]}))
     cols["EbN0_dB"] = grid
     return cols
 
 
 def soft_hardinit_plot(sparcparams, ldpcparams, csv_filename, png_filename, sections, datapoints=10, MIN_ERRORS=100,
-                       MAX_BLOCKS=500, soft_iter=3, threshold=0.6, chunk=64, SIGMA=None, rng=None):
-    """Threshold-initialised exchange sweep (sparc_ldpc.py:1435-1581), sigma grid linspace(0.9, 1.4)."""
+                       MAX_BLOCKS=500, soft_iter=3, threshold=0.6, chunk=64, SIGMA=None, rng=None, group=None):
+    """Threshold-initialised exchange sweep (sparc_ldpc.py:1435-1581), sigma grid linspace(0.9, 1.4).  `group`: as in
+    waterfall()."""
     rng = _rng(rng)
     L, M = sparcparams.L, sparcparams.M
     logm = np.log2(M)
@@ -471,23 +532,25 @@ def soft_hardinit_plot(sparcparams, ldpcparams, csv_filename, png_filename, sect
     for i, sigma in enumerate(SIGMA):
         rows = _pair_driver(D.threshold, SPARCParams(L, M, sigma, p, r_sparc, T), ldpcparams,
                             SPARCParams(L, M, sigma, p, R, T), rng, MIN_ERRORS, MAX_BLOCKS, chunk,
-                            seed=0 if ieee else None, all_zero=not ieee, soft_iter=soft_iter, thr=threshold)
+                            seed=0 if ieee else None, all_zero=not ieee, group=group, soft_iter=soft_iter, thr=threshold)
         nb = len(rows)
         BER_amp[i] = np.sum([r_[0] for r_ in rows], axis=0) / nb
         BER_ldpc[i] = np.sum([r_[1] for r_ in rows], axis=0) / nb
-        BER_plain[i] = sum(r_[2] for r_ in rows) / nb
+        BER_plain[i] = _seqsum(r_[2] for r_ in rows) / nb
     EbN0_dB = 20 * np.log10(1 / (2 * R) * (p / SIGMA ** 2))            # :1531-1533
-    with open(csv_filename, "a") as fh:
-        w = csv.DictWriter(fh, fieldnames=["EbN0_dB", "BER_amp", "BER_ldpc", "BER_plain"])  # :1537
-        w.writeheader()
-        for k in range(datapoints):
-            w.writerow({"EbN0_dB": EbN0_dB[k], "BER_amp": BER_amp[k, :], "BER_ldpc": BER_ldpc[k, :], "BER_plain": BER_plain[k]})
+    if SD.group_info(group)[0] == 0:
+        with open(csv_filename, "a") as fh:
+            w = csv.DictWriter(fh, fieldnames=["EbN0_dB", "BER_amp", "BER_ldpc", "BER_plain"])  # :1537
+            w.writeheader()
+            for k in range(datapoints):
+                w.writerow({"EbN0_dB": EbN0_dB[k], "BER_amp": BER_amp[k, :], "BER_ldpc": BER_ldpc[k, :], "BER_plain": BER_plain[k]})
     return dict(EbN0_dB=EbN0_dB, BER_amp=BER_amp, BER_ldpc=BER_ldpc, BER_plain=BER_plain)
 
 
 def soft_hard_plot(soft, hard, sec, soft_iter, sparcparams, ldpcparams, csv_filename, png_filename, datapoints=10,
-                   MIN_ERRORS=100, MAX_BLOCKS=500, chunk=64, SIGMA=None, rng=None):
-    """Soft vs original-hard exchange sweep (sparc_ldpc.py:1285-1432), sigma grid linspace(0.8, 0.4)."""
+                   MIN_ERRORS=100, MAX_BLOCKS=500, chunk=64, SIGMA=None, rng=None, group=None):
+    """Soft vs original-hard exchange sweep (sparc_ldpc.py:1285-1432), sigma grid linspace(0.8, 0.4).  `group`: as in
+    waterfall()."""
     rng = _rng(rng)
     L, M = sparcparams.L, sparcparams.M
     logm = np.log2(M)
@@ -514,7 +577,7 @@ def soft_hard_plot(soft, hard, sec, soft_iter, sparcparams, ldpcparams, csv_file
             ba, bl = flow(su, y, **kw).ber(tx, su.total_bits)
             return [(ba[j], bl[j]) for j in range(len(blocks))]
 
-        return _mc(rng, lambda: _draw(su, 1, sp.sigma, rng), decode_blocks, stop, MIN_ERRORS, MAX_BLOCKS, chunk)
+        return _mc(rng, lambda: _draw(su, 1, sp.sigma, rng), decode_blocks, stop, MIN_ERRORS, MAX_BLOCKS, chunk, group)
 
     for i, sigma in enumerate(SIGMA):
         sp_c = SPARCParams(L, M, sigma, p, r_sparc, T, a, f, C)
@@ -522,9 +585,12 @@ def soft_hard_plot(soft, hard, sec, soft_iter, sparcparams, ldpcparams, csv_file
         # plain SPARC: exactly MIN_ERRORS runs (:1341-1344)
         su_p = D.make_setup(sp_p, None)
         blocks = [_draw(su_p, 1, sigma, rng) for _ in range(MIN_ERRORS)]
-        tx, y = _transmit(su_p, np.concatenate([b[0] for b in blocks]), np.concatenate([b[1] for b in blocks]))
-        ba, _ = D.plain(su_p, y).ber(tx, su_p.total_bits)
-        out["BER_sparc"][i] = np.sum(ba[:, 0]) / MIN_ERRORS
+
+        def decode_plain(bl):
+            tx, y = _transmit(su_p, np.concatenate([b[0] for b in bl]), np.concatenate([b[1] for b in bl]))
+            return D.plain(su_p, y).ber(tx, su_p.total_bits)[0][:, 0].tolist()
+
+        out["BER_sparc"][i] = np.sum(SD.decode_sharded(decode_plain, blocks, group)) / MIN_ERRORS
         if soft:
             rows = single(D.soft, sp_c, ldpcparams, lambda row: row[1][0] != 0, soft_iter=soft_iter)  # :1359
             out["BER_amp_soft"][i] = np.sum([r_[0] for r_ in rows], axis=0) / len(rows)
@@ -534,7 +600,7 @@ def soft_hard_plot(soft, hard, sec, soft_iter, sparcparams, ldpcparams, csv_file
             out["BER_amp_hard"][i] = np.sum([np.pad(r_[0], (0, 2 - len(r_[0]))) for r_ in rows], axis=0) / len(rows)
             out["BER_ldpc_hard"][i] = np.sum([r_[1][0] for r_ in rows]) / len(rows)
     EbN0_dB = 20 * np.log10(1 / (2 * R) * (p / SIGMA ** 2))
-    with open(csv_filename, "a") as fh:
+    with open(csv_filename if SD.group_info(group)[0] == 0 else os.devnull, "a") as fh:
         if soft:
             w = csv.DictWriter(fh, fieldnames=["EbN0_dB", "BER_sparc", "BER_ldpc_soft", "BER_amp_soft"])  # :1400
             w.writeheader()

@@ -182,8 +182,6 @@ def test_errors_mirror_the_reference():
     Ab, Az, _ = S.sparc_transforms(8, 16, 24)
     with pytest.raises(AssertionError):
         Ab(np.zeros(5))
-    with pytest.raises(NotImplementedError):
-        S.amp(np.zeros((24, 1)), None, np.ones(8), 8, 16, 4, lambda b: b, lambda z: z)
     with pytest.raises(AssertionError):          # LDPC must cover whole sections (sparc_ldpc.py:416)
         S.soft_amp_ldpc_sim(S.SPARCParams(64, 32, 0.5, 4.0, 1, 8), S.LDPCParams("802.16", "5/6", 8), 1)
 
@@ -246,3 +244,69 @@ def test_ber_waterfall_matches_reference_csv():
         else:                           # above the waterfall: rare section errors, LDPC cleans them up
             assert 0.5 < res["ber_amp"][0] / r["BER_amp_1"] < 2.0
             assert res["ber_ldpc"][0] < 5e-5 and res["ber_ldpc"][1] < 5e-5
+
+
+def test_amp_with_foreign_closures_matches_device_loop(oracle):
+    """amp() accepts any Ab / Az callables like the reference (sparc_ldpc.py:189): with the ORACLE's numpy closures
+    of the same operator (foreign to the library) the host loop + device softmax must reproduce the one-kernel
+    decode: same stop index, beta to fp64 rounding; and the reference's own amp() golden trace."""
+    from conftest import golden
+    from sparc_ldpc_b200 import amp_test as AT, sparc_ldpc as S
+    orc = oracle
+    g = golden("amp_small")
+    L, M, P, T, n = 128, 4, 2.0, 64, 256
+    Pl = P / L * np.ones(L)
+    Ab_o, Az_o, _ = orc.sparc_transforms(L, M, n)
+    Ab_d, Az_d, _ = S.sparc_transforms(L, M, n)
+    for k, init in ((0, None), (1, None), (0, g["c1_w_init"])):
+        y = g["c1_%d_y" % k].reshape(-1, 1)
+        bf, tf = AT.amp_test(y, 0, Pl, L, M, T, Ab_o, Az_o, init)
+        bd, td = AT.amp_test(y, 0, Pl, L, M, T, Ab_d, Az_d, init)
+        assert bf.shape == (L * M, 1) and abs(tf - td) <= 2
+        assert np.max(np.abs(bf - bd)) <= 1e-9 * np.max(np.abs(bd))
+    b = S.amp(g["c1_0_y"].reshape(-1, 1), 0, Pl, L, M, T, Ab_o, Az_o)
+    assert np.max(np.abs(b.reshape(-1) - g["c1_0_beta"])) <= 1e-9 * np.max(np.abs(g["c1_0_beta"]))
+    # callables with no relation to the library at all
+    bz = S.amp(np.zeros((24, 1)), None, np.ones(8), 8, 16, 4, lambda b: np.zeros((24, 1)), lambda z: np.zeros((128, 1)))
+    assert bz.shape == (128, 1) and float(np.abs(bz).max()) == 0.0     # tau == last_tau == 0 on the first test (:204)
+
+
+def test_amp_exit_curve_export_then_import(tmp_path):
+    """amp_exit_curve(export_csv_filename=...) writes one (header, row) pair per sample in the reference's layout
+    (amp_exit.py:262-268); amp_exit_curve(import_data=True) reads them back (amp_exit.py:353-398, :550-583) and
+    recomputes the same I_e from histograms alone (E is printed with 8 significant digits, as by the reference)."""
+    from sparc_ldpc_b200 import amp_exit as AE, sparc_ldpc as S
+    L, M = 32, 8
+    sp = S.SPARCParams(L, M, None, 4.0, 1, 64)
+    f = str(tmp_path / "E.csv")
+    # SNRs and I_a values whose rounded keys are distinct (the reference keys on round(I_a, 1) and round(snr))
+    Ia, Ie, poly = AE.amp_exit_curve(sp, 10, 16, 2, 10, 0.7, bin_number=30, export_csv_filename=f,
+                                     rng=np.random.RandomState(5))
+    rows = list(csv.reader(open(f)))
+    assert rows[0] == ["I_a", "snr_dB", "X", "E"] and sum(r == rows[0] for r in rows) == 2 * 4 * 10
+    d = AE.import_E_fromfile(f, 4, 2, L * 3)
+    assert len(d) == 80 and all(len(v.X) == L * 3 and len(v.E) == L * 3 for v in d.values())
+    Ia2, Ie2, poly2 = AE.amp_exit_curve(sp, 10, 16, 2, 10, 0.7, bin_number=30, import_data=True, import_csv_filename=f)
+    assert np.array_equal(Ia, Ia2)
+    # printing E with 8 digits can move a sample across a bin edge: compare on the scale of one sample of 96
+    assert np.max(np.abs(Ie - Ie2)) < 0.05 and np.mean(np.abs(Ie - Ie2)) < 5e-3
+
+
+def test_parity_mode_drivers_sharded_over_two_ranks():
+    """waterfall / soft_hard_plot / soft_hardinit_plot / sim_ldpc / amp_exit_curve with group=: two ranks as two
+    PROCESSES on this one GPU (gloo for the row exchange; on a multi-GPU box the same tool runs one rank per GPU
+    over NCCL).  tools/mp_drivers_check.py asserts, on every rank, that the CSV columns and the final state of the
+    host RNG stream are identical to the one-rank run (sparc_ldpc.py:1217-1251, amp_exit.py:560-595)."""
+    import json
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [_sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tools", "mp_drivers_check.py"), "--same-gpu"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    lines = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert {d["driver"] for d in lines} >= {"waterfall_soft", "waterfall_originalHard", "soft_hard_plot", "soft_hardinit_plot",
+                                            "sim_ldpc", "amp_exit_curve"}
+    assert all(d["identical_on_all_ranks"] for d in lines)
