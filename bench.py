@@ -122,7 +122,7 @@ class Clocks(threading.Thread):
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag.is_set():
+        while not self.stop_flag.is_set() and not os.environ.get("BENCH_NO_CLOCKS"):
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -144,7 +144,33 @@ class Clocks(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def _union_ms(ev0, pairs):
+    """Time during which at least one of the [start, end] event pairs was open (launches of different streams
+    overlap), in ms relative to ev0."""
+    iv = sorted((ev0.elapsed_time(a), ev0.elapsed_time(b)) for a, b in pairs)
+    tot, cs, ce = 0.0, None, None
+    for s_, e_ in iv:
+        if ce is None or s_ > ce:
+            if ce is not None:
+                tot += ce - cs
+            cs, ce = s_, e_
+        else:
+            ce = max(ce, e_)
+    if ce is not None:
+        tot += ce - cs
+    return tot
+
+
+AMP_DESC = {"fast": "fast (fp64 state / transforms / softmax; z and FHT(beta) gathered from 27-bit fixed-point copies; "
+                    "stop at |d tau| <= 2^-27 tau)",
+            "strict": "strict (fp64 throughout, reference add order, exact-equality stop tau == last_tau)"}
+BP_DESC = {"fast": "fast (fp64 messages; the two log(1+exp(-|x|)) terms of every Lxor in single precision)",
+           "strict": "strict (fp64 exp/log as c_ldpc.c:246-247)"}
+
+
 def gpu_arm(args):
+    import ctypes as ct
+
     import torch
     import torch.distributed as dist
 
@@ -158,14 +184,12 @@ def gpu_arm(args):
     dev = torch.device("cuda", local)
 
     from sparc_ldpc_b200 import _lib, decoder as D, engine as E, sparc_ldpc as S
-    from sparc_ldpc_b200.ldpc import get_code
 
     B = args.batch
-    E.AMP_MODE = args.amp_mode
-    E.BP_MODE = args.bp_mode
     sp = S.SPARCParams(L=L, M=M, sigma=SIGMA, p=P, r=R_SPARC, t=T)
     su = D.make_setup(sp, S.LDPCParams(STD, RATE, Z))
     assert su.n == N and su.total_bits - (su.nl - su.kl) == INFO_BITS
+    lxor_per_bp_iteration = int(sum(3 * (int(d) - 2) for d in su.graph.cdeg))     # c_ldpc.c:294-314 per check node
 
     # synthetic codewords: valid LDPC codewords + AWGN from a per-rank seeded host stream (reference draw order)
     rng = np.random.RandomState(1000 + rank)
@@ -177,30 +201,46 @@ def gpu_arm(args):
     errs_host = torch.empty((2 * SOFT_ITER + 1, B), dtype=torch.int32).pin_memory()
     torch.cuda.synchronize()
 
-    amp_events, amp_meta = [], []
-    orig_amp = su.op.amp
+    # every AMP / BP launch is bracketed by CUDA events on its launching stream
+    amp_ev, amp_exec, bp_ev, bp_its = [], [], [], []
+    orig_amp, orig_bp = su.op.amp, su.graph.bp
 
     def timed_amp(*a, **k):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         r = orig_amp(*a, **k)
         e1.record()
-        amp_events.append((e0, e1))
-        amp_meta.append(r.n_exec)
+        amp_ev.append((e0, e1))
+        amp_exec.append(r.n_exec)
         return r
+
+    def timed_bp(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_bp(*a, **k)
+        e1.record()
+        bp_ev.append((e0, e1))
+        bp_its.append(r[1])
+        return r
+
+    su.op.amp, su.graph.bp = timed_amp, timed_bp
+
+    def clear():
+        del amp_ev[:], amp_exec[:], bp_ev[:], bp_its[:]
 
     # The batch is cut into `--streams` slices, each decoded on its own CUDA stream: a slice's dependent chain
     # (AMP -> BP -> AMP ...) is sequential, but the tail of one slice's launch (codewords that run all 64 AMP /
     # 200 BP iterations) overlaps with the next slice's work instead of idling the other SMs.
-    S_ = max(1, min(args.streams, B))
-    bounds = [(i * B) // S_ for i in range(S_ + 1)]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(S_)]
-    tx_sl = [tx[bounds[i]:bounds[i + 1]].contiguous() for i in range(S_)]
+    all_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(args.streams, B)))]
 
-    def step_device(y):
+    def step_device(y, tx_, nstreams):
+        b = y.shape[0]
+        S_ = max(1, min(nstreams, b))
+        bounds = [(i * b) // S_ for i in range(S_ + 1)]
         main = torch.cuda.current_stream()
         outs = []
-        for i, st_ in enumerate(streams):
+        for i in range(S_):
+            st_ = all_streams[i]
             st_.wait_stream(main)
             with torch.cuda.stream(st_):
                 ys = y[bounds[i]:bounds[i + 1]]
@@ -208,9 +248,10 @@ def gpu_arm(args):
                 stages = [st.amp_idx[0]]
                 for j in range(SOFT_ITER):
                     stages += [st.ldpc_idx[j], st.amp_idx[j + 1]]
-                errs = torch.stack([E.count_errors(s, tx_sl[i]) for s in stages])      # [5, b] bit errors per stage
+                txs = tx_[bounds[i]:bounds[i + 1]]
+                errs = torch.stack([E.count_errors(s, txs) for s in stages])      # [5, b] bit errors per stage
                 outs.append((st, errs))
-        for st_ in streams:
+        for st_ in all_streams[:S_]:
             main.wait_stream(st_)
         errs = torch.cat([o[1] for o in outs], dim=1)
         totals = errs.sum(dim=1, dtype=torch.int64)
@@ -220,7 +261,7 @@ def gpu_arm(args):
 
     def step_e2e():
         y = y_host.to(dev, non_blocking=True)
-        sts, errs, totals = step_device(y)
+        sts, errs, totals = step_device(y, tx, args.streams)
         idx_host.copy_(torch.cat([s.ldpc_idx[-1] for s in sts]), non_blocking=True)   # final decisions
         errs_host.copy_(errs, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -231,132 +272,199 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
-    for _ in range(max(args.warmup, 3)):
-        step_device(y_dev)
-    barrier()
-
-    # ---- timed: device-resident inputs
-    su.op.amp = timed_amp
-    clocks = Clocks(local)
-    clocks.start()
-    launches0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    bp_its, last = [], None
-    for _ in range(args.steps):
-        last = step_device(y_dev)
-        for st in last[0]:
-            bp_its.append(st.bp_it)
-    ev1.record()
-    barrier()
-    launches = _lib.launch_count() - launches0
-    ms = ev0.elapsed_time(ev1)
-    su.op.amp = orig_amp
-    # time during which at least one amp_kernel launch was executing: union of the per-launch [start, end]
-    # intervals (launches of different streams overlap), from CUDA events on the launching streams
-    iv = sorted((ev0.elapsed_time(a), ev0.elapsed_time(b)) for a, b in amp_events)
-    amp_ms, cur_s, cur_e = 0.0, None, None
-    for s_, e_ in iv:
-        if cur_e is None or s_ > cur_e:
-            if cur_e is not None:
-                amp_ms += cur_e - cur_s
-            cur_s, cur_e = s_, e_
-        else:
-            cur_e = max(cur_e, e_)
-    if cur_e is not None:
-        amp_ms += cur_e - cur_s
-    n_amp_launch = len(amp_events)
-    exec_iters = float(sum(int(m.sum()) for m in amp_meta))
-    bp_iters = float(sum(int(t.sum()) for its in bp_its for t in its))
-    amp_events.clear()
-
-    # ---- untimed extra step on ONE stream: the amp kernel's share of a serialised step (what an ncu launch
-    # list of this command shows; with several streams the kernel is busy during ~100 % of the step)
-    su.op.amp = timed_amp
-    streams_saved, bounds_saved, tx_saved = streams, bounds, tx_sl
-    streams, bounds, tx_sl = streams[:1], [0, B], [tx]
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    s0.record()
-    step_device(y_dev)
-    s1.record()
-    barrier()
-    share_serial = sum(a.elapsed_time(b) for a, b in amp_events) / s0.elapsed_time(s1)
-    amp_events.clear()
-    del amp_meta[:]
-    streams, bounds, tx_sl = streams_saved, bounds_saved, tx_saved
-    su.op.amp = orig_amp
-
-    # ---- timed: end to end from pinned host buffers
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    clocks.stop_flag.set()
-    clocks.join(2)
-
-    t = torch.tensor([ms, ms_e2e, amp_ms], dtype=torch.float64, device=dev)
-    sums = torch.tensor([exec_iters, bp_iters], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sums)
-    ms, ms_e2e, amp_ms = (float(v) for v in t)
-    exec_iters, bp_iters = (float(v) for v in sums)
-
-    total_cw = B * world * args.steps
-    value = total_cw / (ms / 1e3)
-    e2e = total_cw / (ms_e2e / 1e3)
     peak, peak_src = peak_hbm()
     bytes_per_iter = (2 * L * M + 3 * N) * 8                    # read beta + write beta + read y, read z, write z (fp64)
-    alg_bytes = exec_iters * bytes_per_iter / world             # per rank (ranks run concurrently)
-    achieved = alg_bytes / (amp_ms / 1e3) / 1e9
-    traffic = None   # dram bytes per launch: ncu-measured dram/algorithmic ratio of this kernel x this run's bytes per launch
+    traffic_ratio, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "amp_traffic.json")
     if os.path.isfile(tpath):
         try:
-            traffic = float(json.load(open(tpath))["ratio"]) * alg_bytes / max(n_amp_launch, 1)
+            tj = json.load(open(tpath))
+            traffic_ratio, traffic_src = tj, "profiles/amp_traffic.json"
         except Exception:
-            traffic = None
+            traffic_ratio = None
+
+    def run_mode(amp_mode, bp_mode, steps, warm, warm_batch):
+        """Times `steps` steps with y resident in HBM, one serialised single-stream step (per-launch durations and
+        the kernels' share of a step), and `steps` end-to-end steps from pinned host buffers."""
+        E.AMP_MODE, E.BP_MODE = amp_mode, bp_mode
+        for _ in range(warm):
+            step_device(y_dev[:warm_batch], tx[:warm_batch], args.streams)
+        barrier()
+        clear()
+        clocks = Clocks(local)
+        clocks.start()
+        launches0 = _lib.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        last = None
+        for _ in range(steps):
+            last = step_device(y_dev, tx, args.streams)
+        ev1.record()
+        barrier()
+        launches = _lib.launch_count() - launches0
+        ms = ev0.elapsed_time(ev1)
+        amp_busy_ms = _union_ms(ev0, amp_ev)
+        n_amp_launch = len(amp_ev)
+        exec_iters = float(sum(int(m.sum()) for m in amp_exec))
+        bp_iters = float(sum(int(t.sum()) for t in bp_its))
+        clear()
+
+        # one extra, untimed step on ONE stream: launches serialise, so every event pair is that launch's own
+        # duration (what an ncu launch list of this command shows) and the kernels' share of a step is defined
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s0.record()
+        step_device(y_dev, tx, 1)
+        s1.record()
+        barrier()
+        ser_ms = s0.elapsed_time(s1)
+        ser_amp = [a.elapsed_time(b) for a, b in amp_ev]
+        ser_bp = [a.elapsed_time(b) for a, b in bp_ev]
+        ser_amp_iters = float(sum(int(m.sum()) for m in amp_exec))
+        ser_bp_iters = float(sum(int(t.sum()) for t in bp_its))
+        clear()
+
+        for _ in range(min(2, warm)):
+            step_e2e()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step_e2e()
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        clocks.stop_flag.set()
+        clocks.join(2)
+        clear()
+
+        t = torch.tensor([ms, ms_e2e, amp_busy_ms, ser_ms, sum(ser_amp), sum(ser_bp)], dtype=torch.float64, device=dev)
+        sums = torch.tensor([exec_iters, bp_iters, ser_amp_iters, ser_bp_iters], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(sums)
+        ms, ms_e2e, amp_busy_ms, ser_ms, ser_amp_ms, ser_bp_ms = (float(v) for v in t)
+        exec_iters, bp_iters, ser_amp_iters, ser_bp_iters = (float(v) / world for v in sums)      # per rank
+        total_cw = B * world * steps
+        alg_bytes = exec_iters * bytes_per_iter
+        achieved = alg_bytes / (amp_busy_ms / 1e3) / 1e9
+        n_ser = max(len(ser_amp), 1)
+        rule = _lib.SB_BP_SUMPROD2_FAST if bp_mode == "fast" else _lib.SB_BP_SUMPROD2
+        pk = ct.c_double(0.0)
+        bp_peak = None
+        if _lib.lib().sb_bp_lxor_peak(rule, ct.byref(pk)) == 0:
+            bp_peak = pk.value
+        bp_ach = ser_bp_iters * lxor_per_bp_iteration / (ser_bp_ms / 1e3) if ser_bp_ms > 0 else None
+        pair = (amp_mode == "fast")
+        return {
+            "value": total_cw / (ms / 1e3), "e2e": total_cw / (ms_e2e / 1e3), "ms_per_step": ms / steps, "steps": steps,
+            "launches": int(launches), "errs": last[2].cpu().numpy(), "clocks": clocks.summary(),
+            "mean_amp_iterations_per_decode": exec_iters * world / (3.0 * total_cw),
+            "mean_bp_iterations_per_decode": bp_iters * world / (2.0 * total_cw),
+            "roofline": {
+                "bound": "hbm", "kernel": "sb::p2::amp2_kernel (two codewords per CTA)" if pair else "sb::amp_kernel<9,1,0,0>",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_codeword_iteration": bytes_per_iter,
+                "us_per_codeword_iteration": 1e3 * amp_busy_ms / max(exec_iters, 1),
+                "launches_timed": n_amp_launch,
+                "kernel_busy_ms": amp_busy_ms, "kernel_busy_fraction_of_timed_region": amp_busy_ms / ms,
+                "busy_ms_per_launch": amp_busy_ms / max(n_amp_launch, 1),
+                "algorithmic_bytes_per_launch": alg_bytes / max(n_amp_launch, 1),
+                "serial_step": {"what": "one untimed step on a single stream: launches do not overlap, each event pair is "
+                                        "one launch's own duration", "ms": ser_ms, "amp_launches": len(ser_amp),
+                                "avg_launch_ms": ser_amp_ms / n_ser,
+                                "algorithmic_bytes_per_launch": ser_amp_iters * bytes_per_iter / n_ser,
+                                "achieved": ser_amp_iters * bytes_per_iter / (ser_amp_ms / 1e3) / 1e9,
+                                "frac": ser_amp_iters * bytes_per_iter / (ser_amp_ms / 1e3) / 1e9 / peak,
+                                "kernel_share_of_step": ser_amp_ms / ser_ms, "bp_share_of_step": ser_bp_ms / ser_ms},
+            },
+            "roofline_bp": {
+                "bound": "fp64/sfu instruction rate", "kernel": "sb::bp_kernel_reg<%s>" % ("SUMPROD2_FAST" if bp_mode == "fast" else "SUMPROD2"),
+                "achieved": bp_ach, "peak": bp_peak, "unit": "Lxor/s", "frac": (bp_ach / bp_peak) if (bp_ach and bp_peak) else None,
+                "lxor_per_codeword_iteration": lxor_per_bp_iteration, "launches_timed": len(ser_bp),
+                "avg_launch_ms": ser_bp_ms / max(len(ser_bp), 1),
+                "peak_source": "sb_bp_lxor_peak: register-only loop of the same check-node function on all SMs, measured in this run",
+                "note": "launch duration includes the tail of codewords that run all 200 iterations while the other "
+                        "CTAs have left (hidden by the stream slices in the timed region)"},
+        }
+
+    fast = run_mode(args.amp_mode, args.bp_mode, args.steps, max(args.warmup, 3), B)
+    strict = None
+    if not args.no_strict and (args.amp_mode, args.bp_mode) != ("strict", "strict"):
+        strict = run_mode("strict", "strict", max(1, args.strict_steps), 1, max(148, B // 8))
+    su.op.amp, su.graph.bp = orig_amp, orig_bp
+
+    if traffic_ratio is not None:
+        for rec, key in ((fast, args.amp_mode), (strict, "strict")):
+            if rec is None or key not in traffic_ratio:
+                continue
+            tr = traffic_ratio[key]
+            rl = rec["roofline"]
+            rl["traffic"] = float(tr["ratio"]) * rl["serial_step"]["algorithmic_bytes_per_launch"]
+            rl["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel "
+                                    "(%s; %s) = %.3f x that launch's algorithmic bytes, scaled to serial_step's bytes per launch"
+                                    % (tr.get("kernel", "?"), tr.get("capture", "?"), float(tr["ratio"])))
+
+    shapes = None
+    if rank == 0 or world > 1:
+        if not args.no_shapes:
+            E.AMP_MODE, E.BP_MODE = args.amp_mode, args.bp_mode
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_shapes
+                shapes = bench_shapes.run_all(rank, world, dev, peak, quick=True)
+            except Exception as ex:  # the shapes block is additional information, never the headline
+                shapes = {"failed": repr(ex)}
 
     if rank == 0:
-        errs_tot = last[2].cpu().numpy()
         nbits = B * world * su.total_bits
+        amp_mode, bp_mode = args.amp_mode, args.bp_mode
         line = {
-            "metric": METRIC, "value": value, "unit": "codewords/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "info_mbit_per_s": value * INFO_BITS / 1e6,
-            "config": {"workload": WORKLOAD, "codewords_per_step_per_gpu": B, "sigma": SIGMA, "amp_T": T, "streams": S_,
-                       "amp_mode": args.amp_mode + (" (fp64; z and FHT(beta) gathered from 27-bit fixed-point copies)"
-                                                    if args.amp_mode == "fast" else " (fp64, reference add order)"),
-                       "bp_mode": args.bp_mode + (" (fp64 messages; the two log(1+exp(-|x|)) terms of every Lxor in single precision)"
-                                                  if args.bp_mode == "fast" else " (fp64 exp/log as c_ldpc.c:246-247)"),
+            "metric": METRIC, "value": fast["value"], "unit": "codewords/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": fast["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": ("f64 state/transforms/softmax, q27 fixed-point gathers, f32 BP correction terms"
+                      if (amp_mode, bp_mode) == ("fast", "fast") else "f64"),
+            "data": "synthetic",
+            "info_mbit_per_s": fast["value"] * INFO_BITS / 1e6,
+            "config": {"workload": WORKLOAD, "codewords_per_step_per_gpu": B, "sigma": SIGMA, "amp_T": T, "streams": args.streams,
+                       "amp_mode": AMP_DESC[amp_mode], "bp_mode": BP_DESC[bp_mode],
                        "l2": "working set %.0f MB of beta per GPU per step exceeds the 126 MB L2" % (B * L * M * 8 / 1e6),
-                       "ber_per_stage[amp1,ldpc1,amp2,ldpc2,amp3]": (errs_tot / nbits).tolist(),
-                       "mean_amp_iterations_per_decode": exec_iters / (3.0 * total_cw),
-                       "mean_bp_iterations_per_decode": bp_iters / (2.0 * total_cw)},
-            "e2e": {"value": e2e, "unit": "codewords/s", "h2d_bytes_per_step": int(B * N * 8),
+                       "ber_per_stage[amp1,ldpc1,amp2,ldpc2,amp3]": (fast["errs"] / nbits).tolist(),
+                       "mean_amp_iterations_per_decode": fast["mean_amp_iterations_per_decode"],
+                       "mean_bp_iterations_per_decode": fast["mean_bp_iterations_per_decode"]},
+            "e2e": {"value": fast["e2e"], "unit": "codewords/s", "h2d_bytes_per_step": int(B * N * 8),
                     "d2h_bytes_per_step": int(idx_host.numel() * 4 + errs_host.numel() * 4),
-                    "info_mbit_per_s": e2e * INFO_BITS / 1e6},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "sb::amp_kernel<9>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_codeword_iteration": bytes_per_iter,
-                         "launches_timed": n_amp_launch, "kernel_share_of_step": share_serial,
-                         "kernel_busy_fraction_of_timed_region": amp_ms / ms,
-                         "avg_launch_ms": amp_ms / max(n_amp_launch, 1),
-                         "algorithmic_bytes_per_launch": alg_bytes / max(n_amp_launch, 1),
-                         "co_limiter": "not HBM: the L1 data pipe (2 L n random shared-memory reads + 25 KB of L2-resident table words per section) is 68% busy, issue 47%, fp64 22%; stalls: long-scoreboard (table loads), MIO queue, barrier (profiles/r01_amp_kernel_ncu_full.csv v11, r01_amp_phase_clocks.txt)"},
-            "clocks": clocks.summary(),
+                    "info_mbit_per_s": fast["e2e"] * INFO_BITS / 1e6},
+            "gpu_launches": fast["launches"],
+            "roofline": fast["roofline"], "roofline_bp": fast["roofline_bp"],
+            "clocks": fast["clocks"],
         }
+        line["roofline"]["co_limiter"] = (
+            "not HBM: the L1 / shared-memory data pipe (2 L n random shared-memory reads per codeword-iteration + the "
+            "L2-resident table words) -- ncu l1tex__data_pipe_lsu_wavefronts 78 % of peak, dram/algorithmic bytes 0.93 "
+            "(profiles/r02_amp_kernel_ncu_full.csv)")
+        if strict is not None:
+            line["strict"] = {
+                "what": "the same step in the reference-arithmetic modes the facades default to (amp strict + bp strict), "
+                        "%d timed step(s) after 1 warm-up step on %d codewords" % (strict["steps"], max(148, B // 8)),
+                "amp_mode": AMP_DESC["strict"], "bp_mode": BP_DESC["strict"], "dtype": "f64",
+                "value": strict["value"], "e2e": strict["e2e"], "unit": "codewords/s", "ms_per_step": strict["ms_per_step"],
+                "steps": strict["steps"], "gpu_launches": strict["launches"],
+                "mean_amp_iterations_per_decode": strict["mean_amp_iterations_per_decode"],
+                "mean_bp_iterations_per_decode": strict["mean_bp_iterations_per_decode"],
+                "ber_per_stage[amp1,ldpc1,amp2,ldpc2,amp3]": (strict["errs"] / nbits).tolist(),
+                "roofline": strict["roofline"], "roofline_bp": strict["roofline_bp"], "clocks": strict["clocks"]}
+            line["iterations_ratio_vs_strict"] = (fast["mean_amp_iterations_per_decode"] /
+                                                  strict["mean_amp_iterations_per_decode"])
+            line["speedup_vs_strict"] = {
+                "value": fast["value"] / strict["value"],
+                "from_fewer_amp_iterations": strict["mean_amp_iterations_per_decode"] / fast["mean_amp_iterations_per_decode"],
+                "from_faster_amp_iteration": strict["roofline"]["us_per_codeword_iteration"] / fast["roofline"]["us_per_codeword_iteration"]}
+        if shapes is not None:
+            line["shapes"] = shapes
         if world == 1 and not args.no_cpu:
             try:
                 c = cpu_run(1, 0)
@@ -382,6 +490,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--streams", type=int, default=8, help="slices of the batch decoded on concurrent CUDA streams")
+    ap.add_argument("--no-strict", action="store_true", help="skip the strict/strict record")
+    ap.add_argument("--strict-steps", type=int, default=1, help="timed steps of the strict/strict record")
+    ap.add_argument("--no-shapes", action="store_true", help="skip the per-shape block (BASELINE.json configs)")
     ap.add_argument("--amp-mode", default="fast", choices=["strict", "fast"],
                     help="AMP arithmetic: strict = fp64 in the reference's add order; fast = fp64 with 32-bit "
                          "fixed-point gathers (include/sparc_b200.h SB_AMP_FAST); both pass the parity tests")

@@ -84,6 +84,11 @@ void sb_graph_destroy(sb_graph *g);
 int sb_bp_batch(const sb_graph *g, int rule, const double *ch, int B, double *app, int *it, int max_it,
                 double minsum_factor, void *stream);
 
+/* Measured instruction ceiling of the check-node function for `rule` on the current device: Lxor evaluations per
+ * second of a register-only loop on all SMs (no memory traffic).  bench.py reports the BP kernel's achieved Lxor/s
+ * against it (c_ldpc.c:234-251 evaluated 3 (dc - 2) times per check and iteration, :294-314). */
+int sb_bp_lxor_peak(int rule, double *lxor_per_s);
+
 /* ------------------------------------------------------------------ (2b) SPARC design operator
  * Block sub-sampled Walsh-Hadamard operator of sparc_ldpc.py:81-147, built from the
  * (L, n) uint32 `ordering` table sparc_transforms returns (host pointer). */

@@ -34,6 +34,7 @@ SIGNATURES = {
     "sb_graph_create": (_i, [_vp, _vp, _vp, _i, _i, _i, ct.POINTER(_vp)]),
     "sb_graph_destroy": (None, [_vp]),
     "sb_bp_batch": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _d, _vp]),
+    "sb_bp_lxor_peak": (_i, [_i, ct.POINTER(_d)]),
     "sb_operator_create": (_i, [_vp, _i, _i, _i, ct.POINTER(_vp)]),
     "sb_operator_destroy": (None, [_vp]),
     "sb_fast_tables_check": (_i, [_vp, _i, _i, _i, _vp]),

@@ -406,3 +406,52 @@ extern "C" double Lxfb(double *L, long dc, int corr_flag) {
     cudaFree(d);
     return r;
 }
+
+// ---- measured instruction ceiling of the check-node function (bench.py roofline_bp) ---------------------------
+// Every thread runs 4 independent chains of `iters` dependent Lxor evaluations on register operands: no memory
+// traffic, all SMs, 8 CTAs of 256 threads per SM.  Lxor/s of this loop is what the fp64 / special-function pipes
+// can sustain for the rule -- the ceiling the resident BP kernel is compared with.
+namespace sb {
+template <int RULE>
+__global__ void __launch_bounds__(256) lxor_peak_kernel(int iters, double seed, double *out) {
+    double a0 = seed + 1e-3 * threadIdx.x, a1 = -a0 * 0.7, a2 = a0 * 1.3, a3 = -a0 * 0.4;
+    const double b0 = 0.9 + 1e-4 * blockIdx.x, b1 = -1.7, b2 = 2.3, b3 = -0.35;
+    for (int i = 0; i < iters; i++) {
+        a0 = lxor_rule<RULE>(a0, b0) + b1;
+        a1 = lxor_rule<RULE>(a1, b1) + b2;
+        a2 = lxor_rule<RULE>(a2, b2) + b3;
+        a3 = lxor_rule<RULE>(a3, b3) + b0;
+    }
+    if (a0 + a1 + a2 + a3 == 12345.678) out[0] = a0;  // keeps the chains alive
+}
+}  // namespace sb
+
+extern "C" int sb_bp_lxor_peak(int rule, double *lxor_per_s) {
+    if (!lxor_per_s || (rule != SB_BP_SUMPROD2 && rule != SB_BP_SUMPROD2_FAST && rule != SB_BP_MINSUM))
+        return sb::fail(SB_EINVAL, "sb_bp_lxor_peak: rule must be SB_BP_SUMPROD2, SB_BP_SUMPROD2_FAST or SB_BP_MINSUM%s", "");
+    int dev = 0, nsm = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    SB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    double *out = nullptr;
+    SB_CUDA(cudaMalloc(&out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    SB_CUDA(cudaEventCreate(&e0));
+    SB_CUDA(cudaEventCreate(&e1));
+    const int grid = nsm * 8, iters = rule == SB_BP_SUMPROD2 ? 512 : 4096;
+    float ms = 0.f;
+    for (int rep = 0; rep < 2; rep++) {  // first pass warms up
+        SB_CUDA(cudaEventRecord(e0));
+        if (rule == SB_BP_SUMPROD2) sb::lxor_peak_kernel<SB_BP_SUMPROD2><<<grid, 256>>>(iters, 0.37, out);
+        else if (rule == SB_BP_SUMPROD2_FAST) sb::lxor_peak_kernel<SB_BP_SUMPROD2_FAST><<<grid, 256>>>(iters, 0.37, out);
+        else sb::lxor_peak_kernel<SB_BP_MINSUM><<<grid, 256>>>(iters, 0.37, out);
+        SB_LAUNCHED();
+        SB_CUDA(cudaEventRecord(e1));
+        SB_CUDA(cudaEventSynchronize(e1));
+        SB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *lxor_per_s = 4.0 * iters * 256.0 * grid / (ms * 1e-3);
+    return SB_OK;
+}

@@ -916,4 +916,4 @@ def test_pair_kernel_equals_single_codeword_fast_kernel(Eng, S, shape):
     err = relinf(ba.reshape(-1), bb_.reshape(-1))
     print("pair vs single %s full decode: %d of %d converge, iterations %d..%d, max rel beta diff %.2e"
           % (shape, conv.sum(), nb, ia.min(), ia.max(), err))
-    assert err < 1e-7
+    assert err < 1e-6   # (both kernels are FAST: quantisation floor 2^-27 per iteration; tau^2 and |beta|^2 are summed over different thread partitions)
