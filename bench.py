@@ -515,10 +515,11 @@ def main():
     os.dup2(real_stdout, 1)
     os.close(real_stdout)
     lines = [ln for ln in out.getvalue().splitlines() if ln.strip()]
-    for ln in lines[:-1]:
+    result = lines[-1] if (lines and lines[-1].lstrip().startswith("{")) else None   # rank 0's JSON line; other ranks have none
+    for ln in (lines[:-1] if result else lines):
         print(ln, file=sys.stderr)
-    if lines:
-        print(lines[-1], flush=True)
+    if result:
+        print(result, flush=True)
 
 
 if __name__ == "__main__":

@@ -33,6 +33,7 @@ ap.add_argument("--p2p", action="store_true", help="exchange over peer memory in
 ap.add_argument("--same-gpu", action="store_true", help="all ranks on GPU 0, gloo for the host-side rendezvous")
 ap.add_argument("--check", action="store_true", help="run both exchanges and require identical results")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--json", default="", help="rank 0 writes a summary record (JSON) of the last repetition to this file")
 args = ap.parse_args()
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -121,10 +122,23 @@ for rep in range(args.reps):
         allreduce_any(ms, dist.ReduceOp.MAX)
     if rank == 0:
         its = int(res.n_exec.max())
+        last = dict(world=world, exchange=("none" if world == 1 else ("peer-memory push (sb_dense_amp_batch_p2p)" if args.p2p else "NCCL all-reduce (sb_dense_amp_batch_sharded)")),
+                    L=L, M=M, n=n, B=B, sections_per_rank=Ll, ms=float(ms), iterations=its, ms_per_iteration=float(ms) / max(its, 1),
+                    exchange_bytes_per_iteration_per_rank=(B * n + B) * 8 * (world - 1 if args.p2p else (2 * (world - 1) / world if world > 1 else 0)),
+                    payload_bytes=(B * n + B) * 8, section_error_rate=float(errs) / (B * L),
+                    matrix_bytes_per_rank_bf16x3_both_orientations=int(2 * 3 * 2 * n * Ll * M),
+                    beta_sha=__import__("hashlib").sha256(res.beta.cpu().numpy().tobytes()).hexdigest()[:16])
         print("world %d rep %d: %.2f ms for %d codewords x %d iterations (L=%d M=%d n=%d, %d sections per rank), "
               "section error rate %.4f, %s of %.2f MB per iteration"
               % (world, rep, float(ms), B, its, L, M, n, Ll, float(errs) / (B * L),
                  "peer-memory push" if args.p2p else "all-reduce", (B * n + B) * 8 / 1e6))
+if rank == 0 and args.json:
+    import json
+    if args.check and world > 1:
+        last["peer_memory_vs_allreduce_max_rel_beta_diff"] = rel
+        last["peer_memory_repeatable_bitwise"] = bool(same)
+    with open(args.json, "w") as fh:
+        json.dump(last, fh, indent=1)
 if peers is not None:
     peers.close()
 if world > 1:
