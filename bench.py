@@ -163,6 +163,8 @@ def _union_ms(ev0, pairs):
 
 AMP_DESC = {"fast": "fast (fp64 state / transforms / softmax; z and FHT(beta) gathered from 27-bit fixed-point copies; "
                     "stop at |d tau| <= 2^-27 tau)",
+            "f64": "f64 (fp64 throughout, exact-equality stop tau == last_tau; gathers summed in a bank-scheduled order: "
+                   "differs from strict by fp64 summation-order noise ~1e-15 per iteration; the facades' default)",
             "strict": "strict (fp64 throughout, reference add order, exact-equality stop tau == last_tau)"}
 BP_DESC = {"fast": "fast (fp64 messages; the two log(1+exp(-|x|)) terms of every Lxor in single precision)",
            "strict": "strict (fp64 exp/log as c_ldpc.c:246-247)"}
@@ -356,14 +358,16 @@ def gpu_arm(args):
         if _lib.lib().sb_bp_lxor_peak(rule, ct.byref(pk)) == 0:
             bp_peak = pk.value
         bp_ach = ser_bp_iters * lxor_per_bp_iteration / (ser_bp_ms / 1e3) if ser_bp_ms > 0 else None
-        pair = (amp_mode == "fast")
+        kname = {"fast": "sb::p2::amp2_kernel<false> (two codewords per CTA, q27 gathers)",
+                 "f64": "sb::p2::amp2_kernel<true> (one codeword per CTA, fp64 gathers)",
+                 "strict": "sb::amp_kernel<9,1,0,0> (reference add order)"}[amp_mode]
         return {
             "value": total_cw / (ms / 1e3), "e2e": total_cw / (ms_e2e / 1e3), "ms_per_step": ms / steps, "steps": steps,
             "launches": int(launches), "errs": last[2].cpu().numpy(), "clocks": clocks.summary(),
             "mean_amp_iterations_per_decode": exec_iters * world / (3.0 * total_cw),
             "mean_bp_iterations_per_decode": bp_iters * world / (2.0 * total_cw),
             "roofline": {
-                "bound": "hbm", "kernel": "sb::p2::amp2_kernel (two codewords per CTA)" if pair else "sb::amp_kernel<9,1,0,0>",
+                "bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_codeword_iteration": bytes_per_iter,
@@ -391,13 +395,14 @@ def gpu_arm(args):
         }
 
     fast = run_mode(args.amp_mode, args.bp_mode, args.steps, max(args.warmup, 3), B)
-    strict = None
+    strict = f64 = None
     if not args.no_strict and (args.amp_mode, args.bp_mode) != ("strict", "strict"):
+        f64 = run_mode("f64", "strict", max(1, args.strict_steps), 1, max(148, B // 8))
         strict = run_mode("strict", "strict", max(1, args.strict_steps), 1, max(148, B // 8))
     su.op.amp, su.graph.bp = orig_amp, orig_bp
 
     if traffic_ratio is not None:
-        for rec, key in ((fast, args.amp_mode), (strict, "strict")):
+        for rec, key in ((fast, args.amp_mode), (f64, "f64"), (strict, "strict")):
             if rec is None or key not in traffic_ratio:
                 continue
             tr = traffic_ratio[key]
@@ -446,23 +451,30 @@ def gpu_arm(args):
             "not HBM: the L1 / shared-memory data pipe (2 L n random shared-memory reads per codeword-iteration + the "
             "L2-resident table words) -- ncu l1tex__data_pipe_lsu_wavefronts 78 % of peak, dram/algorithmic bytes 0.93 "
             "(profiles/r02_amp_kernel_ncu_full.csv)")
+        def ref_record(rec, amp_key):
+            return {
+                "what": "the same step with amp %s + bp strict, %d timed step(s) after 1 warm-up step on %d codewords"
+                        % (amp_key, rec["steps"], max(148, B // 8)),
+                "amp_mode": AMP_DESC[amp_key], "bp_mode": BP_DESC["strict"], "dtype": "f64",
+                "value": rec["value"], "e2e": rec["e2e"], "unit": "codewords/s", "ms_per_step": rec["ms_per_step"],
+                "steps": rec["steps"], "gpu_launches": rec["launches"],
+                "mean_amp_iterations_per_decode": rec["mean_amp_iterations_per_decode"],
+                "mean_bp_iterations_per_decode": rec["mean_bp_iterations_per_decode"],
+                "ber_per_stage[amp1,ldpc1,amp2,ldpc2,amp3]": (rec["errs"] / nbits).tolist(),
+                "roofline": rec["roofline"], "roofline_bp": rec["roofline_bp"], "clocks": rec["clocks"]}
+
         if strict is not None:
-            line["strict"] = {
-                "what": "the same step in the reference-arithmetic modes the facades default to (amp strict + bp strict), "
-                        "%d timed step(s) after 1 warm-up step on %d codewords" % (strict["steps"], max(148, B // 8)),
-                "amp_mode": AMP_DESC["strict"], "bp_mode": BP_DESC["strict"], "dtype": "f64",
-                "value": strict["value"], "e2e": strict["e2e"], "unit": "codewords/s", "ms_per_step": strict["ms_per_step"],
-                "steps": strict["steps"], "gpu_launches": strict["launches"],
-                "mean_amp_iterations_per_decode": strict["mean_amp_iterations_per_decode"],
-                "mean_bp_iterations_per_decode": strict["mean_bp_iterations_per_decode"],
-                "ber_per_stage[amp1,ldpc1,amp2,ldpc2,amp3]": (strict["errs"] / nbits).tolist(),
-                "roofline": strict["roofline"], "roofline_bp": strict["roofline_bp"], "clocks": strict["clocks"]}
+            # strict = the reference's arithmetic AND add order; f64 = the same arithmetic type and stop rule with
+            # scheduled gathers, the mode the reference-facing facades run by default (engine.AMP_MODE)
+            line["strict"] = ref_record(strict, "strict")
+            line["f64"] = ref_record(f64, "f64")
             line["iterations_ratio_vs_strict"] = (fast["mean_amp_iterations_per_decode"] /
                                                   strict["mean_amp_iterations_per_decode"])
             line["speedup_vs_strict"] = {
                 "value": fast["value"] / strict["value"],
                 "from_fewer_amp_iterations": strict["mean_amp_iterations_per_decode"] / fast["mean_amp_iterations_per_decode"],
-                "from_faster_amp_iteration": strict["roofline"]["us_per_codeword_iteration"] / fast["roofline"]["us_per_codeword_iteration"]}
+                "from_faster_amp_iteration": strict["roofline"]["us_per_codeword_iteration"] / fast["roofline"]["us_per_codeword_iteration"],
+                "f64_over_strict": f64["value"] / strict["value"], "fast_over_f64": fast["value"] / f64["value"]}
         if shapes is not None:
             line["shapes"] = shapes
         if world == 1 and not args.no_cpu:

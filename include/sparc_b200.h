@@ -105,6 +105,7 @@ int sb_fast_tables_check(const uint32_t *ordering_host, int L, int M, int n, lon
  * L % 8 == 0; csrc/amp2.cu): every (bin, sign half) lists exactly its rows, every (8-section group, row) its 8
  * (section, column, sign) terms.  Returns 0 = verified, 1 = the shape has no pair tables, <0 = error. */
 int sb_pair_tables_check(const uint32_t *ordering_host, int L, int M, int n, long *stats);
+int sb_pair_tables_check_f64(const uint32_t *ordering_host, int L, int M, int n, long *stats); /* the fp64 tables of SB_AMP_F64 */
 
 /* pyfht.fht_inplace (sparc_ldpc.py:14-29, :69, :76): HOST pointer, N a power of two, transformed in place. */
 int sb_fht_inplace_host(double *x, long N);
@@ -135,6 +136,11 @@ int sb_onehot_apply_batch(const sb_operator *op, const int *idx, const double *P
                            z update and tau^2 stay fp64.  beta / tau^2 agree with STRICT to ~1e-8 relative.  The
                            stop rule becomes |tau - last_tau| <= 2^-27 tau (tau cannot reach an exact fixed point
                            above the quantisation floor), so `iters` is smaller than in STRICT mode.                */
+#define SB_AMP_F64 2    /* fp64 everywhere and the reference's exact-equality stop rule, like STRICT, but the two gathers add
+                           their terms in an order chosen for conflict-free shared-memory access (as FAST does with its
+                           integers): beta / tau^2 differ from STRICT by fp64 summation-order noise (~1e-15 relative per
+                           iteration).  M = 512, w/M <= 16, n <= 4608, L % 8 == 0, all sections active: the warp-specialised
+                           kernel of csrc/amp2.cu on fp64 values, one codeword per CTA; any other call runs STRICT.       */
 /* FAST mode has two kernels: one CTA per codeword (any shape) and, for M = 512 with w/M <= 16, n <= 4608, L % 8 == 0
  * and all sections active, a warp-specialised kernel that decodes two codewords per CTA (csrc/amp2.cu; same
  * arithmetic, A beta / A^T z bit-identical).  sb_amp_pair_enable(0) forces the first for every shape (A/B timing,

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("SPARC_B200_LIB") or os.path.join(_HERE, "libsparc_b20
 
 SB_BP_SUMPROD2, SB_BP_SUMPROD, SB_BP_MINSUM, SB_BP_SUMPROD2_FAST = 0, 1, 2, 3
 SB_AMP_STOPPED, SB_AMP_REF_NAN = 1, 2
-SB_AMP_STRICT, SB_AMP_FAST = 0, 1
+SB_AMP_STRICT, SB_AMP_FAST, SB_AMP_F64 = 0, 1, 2
 SB_MAX_ITCOUNT = 200
 
 _lib = None
@@ -44,6 +44,7 @@ SIGNATURES = {
     "sb_Az_batch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "sb_onehot_apply_batch": (_i, [_vp, _vp, _vp, _vp, _d, _i, _vp, _vp]),
     "sb_amp_pair_enable": (_i, [_i]),
+    "sb_pair_tables_check_f64": (_i, [_vp, _i, _i, _i, _vp]),
     "sb_amp_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_sp2bp_llr_batch": (_i, [_vp, _l, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _l, _vp]),
     "sb_bp2sp_prior_batch": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),

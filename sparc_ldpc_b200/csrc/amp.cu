@@ -4,6 +4,7 @@
 #include "sched.h"
 
 #include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -216,10 +217,16 @@ struct PairTables {
 
 static bool pair_shape_ok(int L, int M, int n, int H) { return M == 512 && H <= 16 && n <= 4608 && n >= 32 && L % 8 == 0; }
 
-static void build_pair_tables(const uint32_t *ordering, int L, int M, int n, int H, PairTables &pt) {
+// f64 = 0: 4-byte words, pools of 32 lanes x 32 banks (the FAST pair kernel).
+// f64 = 1: the same kernel structure on fp64 values (SB_AMP_F64: one codeword per CTA, 8-byte words): a warp-wide
+//          LDS.64 is served half-warp by half-warp, so a pool is 16 lanes x 16 eight-byte banks; fold entries are
+//          byte offsets k * 8 into the fp64 z plane [n | 32 zero words], gather entries slot * 4096 + word * 8 | sign
+//          << 15 into a group buffer [8 slots][512 doubles].
+static void build_pair_tables(const uint32_t *ordering, int L, int M, int n, int H, PairTables &pt, int f64 = 0) {
     if (!pair_shape_ok(L, M, n, H)) return;
     pt.ok = 1;
     const int logM = 9, TEAM = 32, EPT = 16;
+    const int LG = f64 ? 16 : 32, ESZ = f64 ? 8 : 4;  // lanes (= banks) per pool, bytes per element
     pt.inv2.assign((size_t)L * M * 16, 0);
     std::vector<long> stat((size_t)L * 2, 0);
     parallel_for(L, [&](int l0, int l1) {
@@ -234,24 +241,25 @@ static void build_pair_tables(const uint32_t *ordering, int L, int M, int n, int
                 bins[(size_t)(__builtin_popcount(r / M) & 1) * M + r % M].push_back(k);
             }
             for (int e = 0; e < EPT; e++)
-                for (int sg = 0; sg < 2; sg++) {
-                    E.clear();
-                    for (int q = 0; q < TEAM; q++)
-                        for (int k : bins[(size_t)sg * M + fast_bin(logM, TEAM, e, q)]) E.push_back(PoolEdge{q, k & 31, k, 0});
-                    ps.run_best(E, 8);
-                    stat[(size_t)l * 2] += 8;
-                    stat[(size_t)l * 2 + 1] += PoolScheduler::cost(E, 8);
-                    std::fill(used.begin(), used.end(), 0);
-                    for (const PoolEdge &pe : E) used[(size_t)pe.step * 32 + pe.bank] = 1;
-                    uint16_t *dst = pt.inv2.data() + (((size_t)l * EPT + e) * 2 + sg) * TEAM * 8;
-                    for (int t = 0; t < 8; t++) {  // idle slots read a zero word in a bank no real term of the step uses
-                        int fb = 0;
-                        for (int b = 0; b < 32; b++) if (!used[(size_t)t * 32 + b]) { fb = b; break; }
-                        const int zero_word = n + ((fb - n) & 31);
-                        for (int q = 0; q < TEAM; q++) dst[q * 8 + t] = (uint16_t)(zero_word * 4);
+                for (int sg = 0; sg < 2; sg++)
+                    for (int h = 0; h < TEAM / LG; h++) {  // one pool per (half-)warp
+                        E.clear();
+                        for (int q = 0; q < LG; q++)
+                            for (int k : bins[(size_t)sg * M + fast_bin(logM, TEAM, e, h * LG + q)]) E.push_back(PoolEdge{q, k % LG, k, 0});
+                        ps.run_best(E, 8);
+                        stat[(size_t)l * 2] += 8;
+                        stat[(size_t)l * 2 + 1] += PoolScheduler::cost(E, 8);
+                        std::fill(used.begin(), used.end(), 0);
+                        for (const PoolEdge &pe : E) used[(size_t)pe.step * 32 + pe.bank] = 1;
+                        uint16_t *dst = pt.inv2.data() + ((((size_t)l * EPT + e) * 2 + sg) * TEAM + h * LG) * 8;
+                        for (int t = 0; t < 8; t++) {  // idle slots read a zero word in a bank no real term of the step uses
+                            int fb = 0;
+                            for (int b = 0; b < LG; b++) if (!used[(size_t)t * 32 + b]) { fb = b; break; }
+                            const int zero_word = n + ((fb - n) & (LG - 1));
+                            for (int q = 0; q < LG; q++) dst[q * 8 + t] = (uint16_t)(zero_word * ESZ);
+                        }
+                        for (const PoolEdge &pe : E) dst[pe.lane * 8 + pe.step] = (uint16_t)(pe.id * ESZ);
                     }
-                    for (const PoolEdge &pe : E) dst[pe.lane * 8 + pe.step] = (uint16_t)(pe.id * 4);
-                }
         }
     });
     for (int l = 0; l < L; l++) { pt.fold_steps += stat[(size_t)l * 2]; pt.fold_wavefronts += stat[(size_t)l * 2 + 1]; }
@@ -262,15 +270,15 @@ static void build_pair_tables(const uint32_t *ordering, int L, int M, int n, int
         PoolScheduler ps;
         std::vector<PoolEdge> E;
         for (int g = g0; g < g1; g++)
-            for (int k0 = 0; k0 < n; k0 += 32) {
+            for (int k0 = 0; k0 < n; k0 += LG) {
                 E.clear();
-                const int nl = (n - k0 < 32) ? n - k0 : 32;
+                const int nl = (n - k0 < LG) ? n - k0 : LG;
                 for (int q = 0; q < nl; q++)
                     for (int i = 0; i < 8; i++) {
                         const uint32_t r = ordering[(size_t)(g * 8 + i) * n + k0 + q];
                         const uint32_t lo = r % M, sg = __builtin_popcount(r / M) & 1;
-                        const uint32_t off = (uint32_t)i * 4096u + (fq_word(logM, lo) << 2);
-                        E.push_back(PoolEdge{q, (int)((off >> 2) & 31), (int)(off | (sg << 15)), 0});
+                        const uint32_t word = fq_word(logM, lo), off = (uint32_t)i * 4096u + word * (uint32_t)ESZ;
+                        E.push_back(PoolEdge{q, (int)(word % (uint32_t)LG), (int)(off | (sg << 15)), 0});
                     }
                 ps.run_best(E, 8);
                 gstat[(size_t)g * 2] += 8;
@@ -281,7 +289,7 @@ static void build_pair_tables(const uint32_t *ordering, int L, int M, int n, int
     for (int g = 0; g < G; g++) { pt.gather_steps += gstat[(size_t)g * 2]; pt.gather_wavefronts += gstat[(size_t)g * 2 + 1]; }
 }
 
-int launch_amp2(const sb_operator *op, const AmpArgs &a, int B, cudaStream_t st);  // amp2.cu
+int launch_amp2(const sb_operator *op, const AmpArgs &a, int B, int f64, cudaStream_t st);  // amp2.cu
 
 }  // namespace sb
 
@@ -336,7 +344,8 @@ extern "C" int sb_operator_create(const uint32_t *ordering, int L, int M, int n,
             }
         }
     }
-    op->p2ok = 0; op->inv2 = nullptr; op->fwd2 = nullptr;
+    op->p2ok = 0; op->inv2 = nullptr; op->fwd2 = nullptr; op->inv2d = nullptr; op->fwd2d = nullptr; op->p2d_state = 0;
+    op->h_ordering = nullptr;
     if (op->qok) {  // pair-kernel tables
         PairTables pt;
         build_pair_tables(ordering, L, M, n, op->H, pt);
@@ -349,6 +358,9 @@ extern "C" int sb_operator_create(const uint32_t *ordering, int L, int M, int n,
                 return fail(SB_ENOMEM, "sb_operator_create: cudaMalloc (pair tables) failed%s", "");
             }
             op->p2ok = 1;
+            // the fp64 tables of SB_AMP_F64 are built on first use (ensure_f64_tables): keep the ordering
+            op->h_ordering = (uint32_t *)malloc((size_t)L * n * sizeof(uint32_t));
+            if (op->h_ordering) memcpy(op->h_ordering, ordering, (size_t)L * n * sizeof(uint32_t));
         }
     }
     cudaError_t e1 = cudaMalloc(&op->fwd, nf * 2), e2 = cudaMalloc(&op->inv, ni * 2), e3 = cudaMalloc(&op->fwd8, n8 * 2);
@@ -375,21 +387,25 @@ extern "C" void sb_operator_destroy(sb_operator *op) {
     cudaFree(op->fwdq);
     cudaFree(op->inv2);
     cudaFree(op->fwd2);
+    cudaFree(op->inv2d);
+    cudaFree(op->fwd2d);
+    free(op->h_ordering);
     delete op;
 }
 
 // Test hook (no GPU needed) for the pair-kernel tables: every (bin, sign half) of every section lists exactly its
 // rows, every (8-section group, row) exactly its 8 (slot, column, sign) terms.  stats[0..3] as sb_fast_tables_check.
 // Returns 0 = verified, 1 = the shape has no pair tables, < 0 = error.
-extern "C" int sb_pair_tables_check(const uint32_t *ordering, int L, int M, int n, long *stats) {
+static int pair_tables_check(const uint32_t *ordering, int L, int M, int n, int f64, long *stats) {
     if (!ordering || L <= 0 || n <= 0 || M < 2 || (M & (M - 1)) || M > 1024 || n >= 65534)
         return fail(SB_EINVAL, "sb_pair_tables_check: bad shape%s (M=%ld)", "", M);
     int w = 1;
     while (w < (M + 1 > n + 1 ? M + 1 : n + 1)) w <<= 1;
     PairTables pt;
-    build_pair_tables(ordering, L, M, n, w / M, pt);
+    build_pair_tables(ordering, L, M, n, w / M, pt, f64);
     if (stats) { stats[0] = pt.fold_steps; stats[1] = pt.fold_wavefronts; stats[2] = pt.gather_steps; stats[3] = pt.gather_wavefronts; }
     if (!pt.ok) return 1;
+    const int esh = f64 ? 3 : 2, emask = (1 << esh) - 1;
     std::vector<int> seen(n);
     for (int l = 0; l < L; l++) {
         std::fill(seen.begin(), seen.end(), 0);
@@ -398,8 +414,8 @@ extern "C" int sb_pair_tables_check(const uint32_t *ordering, int L, int M, int 
                 for (int q = 0; q < 32; q++)
                     for (int t = 0; t < 8; t++) {
                         const int o = pt.inv2[((((size_t)l * 16 + e) * 2 + sg) * 32 + q) * 8 + t];
-                        if (o & 3) return fail(SB_EINVAL, "pair tables: unaligned fold offset%s (%ld)", "", o);
-                        const int k = o >> 2;
+                        if (o & emask) return fail(SB_EINVAL, "pair tables: unaligned fold offset%s (%ld)", "", o);
+                        const int k = o >> esh;
                         if (k >= n && k < n + 32) continue;  // zero word
                         if (k >= n + 32) return fail(SB_EINVAL, "pair tables: fold offset out of range%s (%ld)", "", o);
                         const uint32_t r = ordering[(size_t)l * n + k];
@@ -413,8 +429,8 @@ extern "C" int sb_pair_tables_check(const uint32_t *ordering, int L, int M, int 
             unsigned mask = 0;
             for (int t = 0; t < 8; t++) {
                 const uint32_t e = pt.fwd2[((size_t)g * n + k) * 8 + t];
-                const uint32_t sg = e >> 15, off = e & 0x7FFFu, slot = off >> 12, word = (off & 4095u) >> 2;
-                if ((off & 3) || word >= 512) return fail(SB_EINVAL, "pair tables: bad gather offset%s (%ld)", "", e);
+                const uint32_t sg = e >> 15, off = e & 0x7FFFu, slot = off >> 12, word = (off & 4095u) >> esh;
+                if ((off & (uint32_t)emask) || word >= 512) return fail(SB_EINVAL, "pair tables: bad gather offset%s (%ld)", "", e);
                 const uint32_t lo = ((word >> 1) & 15u) * 32u + 2u * (word >> 5) + (word & 1u);  // inverse of fq_word
                 const uint32_t r = ordering[(size_t)(g * 8 + slot) * n + k];
                 if (r % M != lo || (uint32_t)(__builtin_popcount(r / M) & 1) != sg)
@@ -424,6 +440,14 @@ extern "C" int sb_pair_tables_check(const uint32_t *ordering, int L, int M, int 
             if (mask != 0xFFu) return fail(SB_EINVAL, "pair tables: missing gather term%s (group %ld)", "", g);
         }
     return SB_OK;
+}
+
+extern "C" int sb_pair_tables_check(const uint32_t *ordering, int L, int M, int n, long *stats) {
+    return pair_tables_check(ordering, L, M, n, 0, stats);
+}
+// the same check for the fp64 tables of SB_AMP_F64 (pools of 16 lanes x 16 eight-byte banks)
+extern "C" int sb_pair_tables_check_f64(const uint32_t *ordering, int L, int M, int n, long *stats) {
+    return pair_tables_check(ordering, L, M, n, 1, stats);
 }
 
 // Test hook (no GPU needed): builds the FAST-mode tables on the host and verifies that they are a reordering of
@@ -502,14 +526,34 @@ extern "C" int sb_phase_cycles_read(unsigned long long *out16) {
 static std::atomic<int> g_pair_on{[] { const char *e = getenv("SB_AMP_PAIR"); return (e && e[0] == '0') ? 0 : 1; }()};
 extern "C" int sb_amp_pair_enable(int on) { return g_pair_on.exchange(on ? 1 : 0); }
 
+// fp64 tables of the warp-specialised kernel, built once per operator on the first SB_AMP_F64 call
+static std::mutex g_f64_mu;
+static int ensure_f64_tables(sb_operator *op) {
+    std::lock_guard<std::mutex> lk(g_f64_mu);
+    if (op->p2d_state) return op->p2d_state > 0 ? SB_OK : 1;
+    if (!op->p2ok || !op->h_ordering) { op->p2d_state = -1; return 1; }
+    PairTables pt;
+    build_pair_tables(op->h_ordering, op->L, op->M, op->n, op->H, pt, 1);
+    if (!pt.ok) { op->p2d_state = -1; return 1; }
+    SB_CUDA(cudaMalloc(&op->inv2d, pt.inv2.size() * 2));
+    SB_CUDA(cudaMalloc(&op->fwd2d, pt.fwd2.size() * 2));
+    SB_CUDA(cudaMemcpy(op->inv2d, pt.inv2.data(), pt.inv2.size() * 2, cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(op->fwd2d, pt.fwd2.data(), pt.fwd2.size() * 2, cudaMemcpyHostToDevice));
+    free(op->h_ordering);
+    op->h_ordering = nullptr;
+    op->p2d_state = 1;
+    return SB_OK;
+}
+
 extern "C" int sb_amp_batch(const sb_operator *op, const double *y, const double *Pl, const double *beta0,
                             const int *sections, const int *nsec, int B, int T, int mode, double *beta, int *iters,
                             int *n_exec, unsigned *flags, double *tau2_trace, double *scratch, void *stream) {
     if (!op || !y || !Pl || !beta || !iters || !n_exec || !flags || B < 0 || T < 0)
         return fail(SB_EINVAL, "sb_amp_batch: null argument%s", "");
-    if (mode != SB_AMP_STRICT && mode != SB_AMP_FAST) return fail(SB_EINVAL, "sb_amp_batch: unknown mode%s %ld", "", mode);
+    if (mode != SB_AMP_STRICT && mode != SB_AMP_FAST && mode != SB_AMP_F64) return fail(SB_EINVAL, "sb_amp_batch: unknown mode%s %ld", "", mode);
     if ((sections == nullptr) != (nsec == nullptr)) return fail(SB_EINVAL, "sb_amp_batch: sections and nsec go together%s", "");
-    if (mode == SB_AMP_FAST && op->qok && !scratch) return fail(SB_EINVAL, "sb_amp_batch: FAST mode needs a [2][B][n] scratch%s", "");
+    if ((mode == SB_AMP_FAST && op->qok && !scratch) || (mode == SB_AMP_F64 && op->p2ok && !scratch))
+        return fail(SB_EINVAL, "sb_amp_batch: FAST / F64 mode needs a [2][B][n] scratch%s", "");
     if (B == 0) return SB_OK;
     AmpArgs a = base_args(op, sections, nsec);
     a.zscratch = scratch;
@@ -520,7 +564,14 @@ extern "C" int sb_amp_batch(const sb_operator *op, const double *y, const double
     a.dbg = g_dbg;
 #endif
     // FAST, all sections active, M = 512: the warp-specialised two-codeword kernel (amp2.cu)
-    if (mode == SB_AMP_FAST && op->p2ok && sections == nullptr && g_pair_on.load()) return launch_amp2(op, a, B, (cudaStream_t)stream);
+    if (mode == SB_AMP_FAST && op->p2ok && sections == nullptr && g_pair_on.load()) return launch_amp2(op, a, B, 0, (cudaStream_t)stream);
+    // F64: the same kernel structure on fp64 values, one codeword per CTA; shapes / section lists it does not cover
+    // run the order-preserving STRICT kernel (same arithmetic type and stop rule)
+    if (mode == SB_AMP_F64 && op->p2ok && sections == nullptr && g_pair_on.load()) {
+        const int rc = ensure_f64_tables(const_cast<sb_operator *>(op));
+        if (rc == SB_OK) return launch_amp2(op, a, B, 1, (cudaStream_t)stream);
+        if (rc < 0 || rc > 1) return rc;
+    }
     return dispatch(op, a, B, mode == SB_AMP_FAST ? 3 : 0, nullptr, nullptr, (cudaStream_t)stream);
 }
 

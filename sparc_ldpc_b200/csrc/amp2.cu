@@ -26,6 +26,8 @@
 // amp_kernel's FAST path; tau^2 and |beta|^2 are summed over a different thread partition (last-bit differences).
 #include "amp_impl.cuh"
 
+#include <type_traits>
+
 // experiment switches (tools/ab_build2.sh): defaults are the measured best
 #ifndef P2_FOLD_UNROLL
 #define P2_FOLD_UNROLL 2  // unroll factor of the fold's loop over the 16 bins of a lane (code size vs scheduling freedom)
@@ -128,25 +130,32 @@ __device__ __forceinline__ double bmax(double v, double *scratch) {
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ int lds32(const char *p) { return *reinterpret_cast<const int *>(p); }
 
+__device__ __forceinline__ double ldsd(const char *p) { return *reinterpret_cast<const double *>(p); }
+
 // 8 table entries (16 bytes) of one bin half: sums of the two codewords' z words they address
-// (NC = 1: only the plane z0 points at -- the CTA's other slot is empty)
-template <int NC>
-__device__ __forceinline__ void fold8(const uint4 w, const char *z0, int &a0, int &a1) {
+// (NC = 1: only the plane z0 points at -- the CTA's other slot is empty; D: fp64 plane, entries are k * 8)
+template <int NC, bool D, typename V>
+__device__ __forceinline__ void fold8(const uint4 w, const char *z0, V &a0, V &a1) {
     const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const uint32_t lo = wd[i] & 0xFFFFu, hi = wd[i] >> 16;
-        a0 += lds32(z0 + lo) + lds32(z0 + hi);
-        if (NC == 2) a1 += lds32(z0 + ZPLANE + lo) + lds32(z0 + ZPLANE + hi);
+        if constexpr (D) {
+            a0 += ldsd(z0 + lo) + ldsd(z0 + hi);
+        } else {
+            a0 += lds32(z0 + lo) + lds32(z0 + hi);
+            if (NC == 2) a1 += lds32(z0 + ZPLANE + lo) + lds32(z0 + ZPLANE + hi);
+        }
     }
 }
 
 // operator warp `rw` folds z of both codewords into the 512 bins of section l and leaves them in the section's
 // slot of the group buffer: word e*32+q of plane c = bin (q>>1)*32 + 2e + (q&1) (layout B of amp_impl.cuh)
-template <int NC>
+template <int NC, bool D>
 __device__ __forceinline__ void fold_section2(const uint16_t *__restrict__ inv2, int l, int q, const char *z0, char *slot) {
+    using V = typename std::conditional<D, double, int>::type;
     const uint4 *t4 = reinterpret_cast<const uint4 *>(inv2) + (size_t)l * (16 * 2 * 32) + q;
-    int *st = reinterpret_cast<int *>(slot) + q;
+    V *st = reinterpret_cast<V *>(slot) + q;
     // The table words of the next bin are in flight while one bin is reduced.  The loop over the 16 bins is NOT
     // fully unrolled: the kernel's hot code has to fit the instruction caches (the SM's and the GPC's), see the
     // note on code size at role_main.
@@ -155,11 +164,11 @@ __device__ __forceinline__ void fold_section2(const uint16_t *__restrict__ inv2,
     for (int e = 0; e < 16; e++) {
         const int en = (e + 1 < 16) ? e + 1 : e;  // (the last iteration reloads its own words: no branch)
         const uint4 n0 = __ldg(t4 + (2 * en) * 32), n1 = __ldg(t4 + (2 * en + 1) * 32);
-        int p0 = 0, p1 = 0, m0 = 0, m1 = 0;
-        fold8<NC>(c0, z0, p0, p1);  // blocks of even parity: +
-        fold8<NC>(c1, z0, m0, m1);  // blocks of odd parity: -
+        V p0 = 0, p1 = 0, m0 = 0, m1 = 0;
+        fold8<NC, D, V>(c0, z0, p0, p1);  // blocks of even parity: +
+        fold8<NC, D, V>(c1, z0, m0, m1);  // blocks of odd parity: -
         st[e * 32] = p0 - m0;
-        if (NC == 2) st[CWOFF / 4 + e * 32] = p1 - m1;
+        if (!D && NC == 2) st[CWOFF / 4 + e * 32] = p1 - m1;
         c0 = n0;
         c1 = n1;
     }
@@ -173,23 +182,29 @@ __device__ __forceinline__ int sign_mask(uint32_t w) {
     return m;
 }
 
-// 8 entries of (group, row): signed words of both codewords' planes
-template <int NC>
-__device__ __forceinline__ void gather8(const uint4 w, const char *bufg, int &p0, int &p1) {
+// 8 entries of (group, row): signed words of both codewords' planes (D: fp64 words, sign = bit 15 -> bit 63)
+template <int NC, bool D, typename V>
+__device__ __forceinline__ void gather8(const uint4 w, const char *bufg, V &p0, V &p1) {
     const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const uint32_t olo = wd[i] & 0x7FFCu, ohi = (wd[i] >> 16) & 0x7FFCu;
+        if constexpr (D) {
+            const double vlo = ldsd(bufg + (wd[i] & 0x7FF8u)), vhi = ldsd(bufg + ((wd[i] >> 16) & 0x7FF8u));
+            p0 += __hiloint2double(__double2hiint(vlo) ^ (int)((wd[i] << 16) & 0x80000000u), __double2loint(vlo)) +
+                  __hiloint2double(__double2hiint(vhi) ^ (int)(wd[i] & 0x80000000u), __double2loint(vhi));
+        } else {
+            const uint32_t olo = wd[i] & 0x7FFCu, ohi = (wd[i] >> 16) & 0x7FFCu;
 #if P2_SIGN_IMAD
-        // +-1 from bit 15 / bit 31; the signed add is one IMAD on the (idle) fma pipe instead of XOR + IADD3 on the alu pipe
-        const int slo = sign_mask<0x9999>(wd[i]) | 1, shi = sign_mask<0xBBBB>(wd[i]) | 1;
-        p0 += lds32(bufg + olo) * slo + lds32(bufg + ohi) * shi;
-        if (NC == 2) p1 += lds32(bufg + CWOFF + olo) * slo + lds32(bufg + CWOFF + ohi) * shi;
+            // +-1 from bit 15 / bit 31; the signed add is one IMAD on the (idle) fma pipe instead of XOR + IADD3 on the alu pipe
+            const int slo = sign_mask<0x9999>(wd[i]) | 1, shi = sign_mask<0xBBBB>(wd[i]) | 1;
+            p0 += lds32(bufg + olo) * slo + lds32(bufg + ohi) * shi;
+            if (NC == 2) p1 += lds32(bufg + CWOFF + olo) * slo + lds32(bufg + CWOFF + ohi) * shi;
 #else
-        const int mlo = sign_mask<0x9999>(wd[i]), mhi = sign_mask<0xBBBB>(wd[i]);  // 0 / -1 from bit 15 / bit 31
-        p0 += ((lds32(bufg + olo) ^ mlo) - mlo) + ((lds32(bufg + ohi) ^ mhi) - mhi);
-        if (NC == 2) p1 += ((lds32(bufg + CWOFF + olo) ^ mlo) - mlo) + ((lds32(bufg + CWOFF + ohi) ^ mhi) - mhi);
+            const int mlo = sign_mask<0x9999>(wd[i]), mhi = sign_mask<0xBBBB>(wd[i]);  // 0 / -1 from bit 15 / bit 31
+            p0 += ((lds32(bufg + olo) ^ mlo) - mlo) + ((lds32(bufg + ohi) ^ mhi) - mhi);
+            if (NC == 2) p1 += ((lds32(bufg + CWOFF + olo) ^ mlo) - mlo) + ((lds32(bufg + CWOFF + ohi) ^ mhi) - mhi);
 #endif
+        }
     }
 }
 
@@ -204,9 +219,10 @@ __device__ __forceinline__ void gather_preload(const uint16_t *__restrict__ fwd2
 
 // operator thread `ot` adds the 8 sections of group g into its rows k = ot + 256 j of both codewords; the table
 // words of batch b+1 are in flight while batch b is gathered
-template <int NC>
+template <int NC, bool D, typename A>
 __device__ __forceinline__ void gather_group2(const uint16_t *__restrict__ fwd2, int g, int n, int ot, const char *bufg,
-                                              long long (&acc)[NR][2], const uint4 (&w0)[KB]) {
+                                              A (&acc)[NR][2], const uint4 (&w0)[KB]) {
+    using V = typename std::conditional<D, double, int>::type;
     const uint4 *tab = reinterpret_cast<const uint4 *>(fwd2) + (size_t)g * n + ot;
     uint4 w[2][KB];
 #pragma unroll
@@ -232,24 +248,27 @@ __device__ __forceinline__ void gather_group2(const uint16_t *__restrict__ fwd2,
 #endif
 #pragma unroll
         for (int j = 0; j < KB; j++) {
-            int p0 = 0, p1 = 0;  // 8 terms of < 2^27 each
-            gather8<NC>(w[b & 1][j], bufg, p0, p1);
+            V p0 = 0, p1 = 0;  // 8 terms (FAST: of < 2^27 each)
+            gather8<NC, D, V>(w[b & 1][j], bufg, p0, p1);
             acc[b * KB + j][0] += p0;
-            if (NC == 2) acc[b * KB + j][1] += p1;
+            if (!D && NC == 2) acc[b * KB + j][1] += p1;
         }
     }
 }
 
 // transform warp: one section of one codeword.  mode 0: fold result -> FHT -> softmax -> beta -> FHT -> F;
 // mode 1: beta0 -> (copy to beta) -> FHT -> F.  Same arithmetic and order as section_phase<9, *, true> (TRQ path).
-__device__ __forceinline__ void transform_unit(const Args &a, const Slot *sl, int sidx, int q, int *st, int *Sp, int *Sn,
+template <bool D>
+__device__ __forceinline__ void transform_unit(const Args &a, const Slot *sl, int sidx, int q, void *stv, int *Sp, int *Sn,
                                                const double *rtp, double inv_rt_n, double &sq, double &gmax, double &lmin) {
     double x[16];
+    int *st = static_cast<int *>(stv);
+    double *std_ = static_cast<double *>(stv);  // D: the slot holds 512 doubles (fold result in, F out)
     const size_t boff = ((size_t)sl->b * a.L + sidx) * M;
     if (sl->mode == 0) {
         const double zunit = sl->zunit;
 #pragma unroll
-        for (int e = 0; e < 16; e++) x[e] = (double)st[e * 32 + q] * zunit;
+        for (int e = 0; e < 16; e++) x[e] = D ? std_[e * 32 + q] : (double)st[e * 32 + q] * zunit;
         double bv[16];
         const bool fz = sl->first_zero != 0;
         const double *bsrc = a.beta + boff;
@@ -297,38 +316,45 @@ __device__ __forceinline__ void transform_unit(const Args &a, const Slot *sl, in
         }
     }
     fht512_A_to_B(x, q, Sp, Sn);
-    const double fs = sl->fscale;
+    if constexpr (D) {
 #pragma unroll
-    for (int e = 0; e < 16; e++) st[e * 32 + q] = __double2int_rn(x[e] * fs);  // word e*32+q = fq_word(lo)
+        for (int e = 0; e < 16; e++) std_[e * 32 + q] = x[e];  // word e*32+q = fq_word(lo)
+    } else {
+        const double fs = sl->fscale;
+#pragma unroll
+        for (int e = 0; e < 16; e++) st[e * 32 + q] = __double2int_rn(x[e] * fs);  // word e*32+q = fq_word(lo)
+    }
 }
 
 // Operator warps, one pass over the sections: fold group i+1 and gather group i-1 while the transform warps work on
 // group i (same barrier sequence as the transform warps' loop in role_main).  NC = 2: both slots, planes at z0 /
 // z0 + ZPLANE and buf / buf + CWOFF; NC = 1: one slot, z0 and buf point at its planes, sums in acc[.][0].
-template <int NC>
+template <int NC, bool D, typename A>
 __device__ __forceinline__ void ow_pass(const Args &a, int n, int G, int rt, int rw, int q, const char *z0, char *buf,
-                                        bool anyfold, long long (&acc)[NR][2]) {
+                                        bool anyfold, A (&acc)[NR][2]) {
     uint4 pre[KB];  // first table words of the next gather
 #pragma unroll
     for (int j = 0; j < NR; j++) acc[j][0] = acc[j][1] = 0;
-    if (anyfold) fold_section2<NC>(a.inv2, rw, q, z0, buf + rw * SLOT);
+    if (anyfold) fold_section2<NC, D>(a.inv2, rw, q, z0, buf + rw * SLOT);
     if (P2_PRELOAD) gather_preload(a.fwd2, 0, n, rt, pre);
     bar_all();
     for (int i = 0;; i++) {  // (one copy of the gather code: the last trip gathers group G-1 and leaves)
         if (i >= 1) {
             if (!P2_PRELOAD) gather_preload(a.fwd2, i - 1, n, rt, pre);
-            gather_group2<NC>(a.fwd2, i - 1, n, rt, buf + ((i - 1) & 1) * BUF, acc, pre);
+            gather_group2<NC, D, A>(a.fwd2, i - 1, n, rt, buf + ((i - 1) & 1) * BUF, acc, pre);
         }
         if (i == G) break;
         bar_ow();  // every operator warp has finished reading that buffer before group i+1 is folded into it
-        if (i + 1 < G && anyfold) fold_section2<NC>(a.inv2, (i + 1) * S + rw, q, z0, buf + ((i + 1) & 1) * BUF + rw * SLOT);
+        if (i + 1 < G && anyfold) fold_section2<NC, D>(a.inv2, (i + 1) * S + rw, q, z0, buf + ((i + 1) & 1) * BUF + rw * SLOT);
         if (P2_PRELOAD && i >= 1) gather_preload(a.fwd2, i, n, rt, pre);
         bar_all();
     }
 }
 
-template <bool OW>
+template <bool OW, bool D>
 __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, const double P, const double fscale_q) {
+    constexpr int NSLOT = D ? 1 : 2;  // D: one fp64 codeword per CTA (its z plane takes the room of the two int32 planes)
+    using A = typename std::conditional<D, double, long long>::type;
     const int tid = threadIdx.x, q = tid & 31, n = a.n, L = a.L, G = L / S;
     const int rt = OW ? tid : tid - NOW, rw = rt >> 5;  // thread / warp index inside the role
     char *zq = reinterpret_cast<char *>(smem);
@@ -339,14 +365,16 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
     int *misc = reinterpret_cast<int *>(slot + 2);
     double *rtp = reinterpret_cast<double *>(misc + 16);
     const double nd = (double)n, rt_n = sqrt(nd), inv_rt_n = 1.0 / rt_n;
-    double *zf = a.zscratch + (size_t)blockIdx.x * 2 * n;  // fp64 z of the two slots: [2][n], rows owned by one thread
-    long long acc[NR][2];  // operator warps only
+    // fp64 z of the slots.  FAST: [2][n] in global scratch, rows owned by one thread (the shared planes hold the
+    // fixed-point copies); D: the shared plane itself
+    double *zf = D ? reinterpret_cast<double *>(zq) : a.zscratch + (size_t)blockIdx.x * 2 * n;
+    A acc[NR][2];  // operator warps only (D: [.][0] only)
     bool exhausted = false;
 
     for (;;) {
         // ---------------- iteration boundary: refill free slots, tau and the stop rule, fixed-point copy of z
 #pragma unroll 1
-        for (int c = 0; c < 2; c++) {
+        for (int c = 0; c < NSLOT; c++) {
             Slot *sl = slot + c;
             double *zc = zf + (size_t)c * n;
             for (;;) {
@@ -373,23 +401,25 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
                             for (int k = rt; k < n; k += NOW) zc[k] = y[k];
                         }
                         bar_all();
-                    } else {  // |FHT_M(beta0_l)| <= sum_j |beta0_l[j]|: one streaming pass gives the fixed-point scale
-                        const double *b0 = a.beta0 + (size_t)b * L * M;
-                        double bound = 0.0;
-                        for (int sidx = tid >> 5; sidx < L; sidx += 16) {
-                            double s1 = 0.0;
-                            for (int j = q; j < M; j += 32) s1 += fabs(b0[(size_t)sidx * M + j]);
+                    } else {
+                        if constexpr (!D) {  // |FHT_M(beta0_l)| <= sum_j |beta0_l[j]|: one streaming pass gives the fixed-point scale
+                            const double *b0 = a.beta0 + (size_t)b * L * M;
+                            double bound = 0.0;
+                            for (int sidx = tid >> 5; sidx < L; sidx += 16) {
+                                double s1 = 0.0;
+                                for (int j = q; j < M; j += 32) s1 += fabs(b0[(size_t)sidx * M + j]);
 #pragma unroll
-                            for (int d = 16; d >= 1; d >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, d);
-                            bound = fmax(bound, s1);
+                                for (int d = 16; d >= 1; d >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+                                bound = fmax(bound, s1);
+                            }
+                            const double bm = bmax(bound, red);
+                            if (tid == 0) {
+                                const double fs = scalbn(1.0, 27 - ceil_exp(bm * (1.0 + 1e-6)));
+                                sl->fscale = fs;
+                                sl->funit = 1.0 / fs;
+                            }
                         }
-                        const double bm = bmax(bound, red);
-                        if (tid == 0) {
-                            const double fs = scalbn(1.0, 27 - ceil_exp(bm * (1.0 + 1e-6)));
-                            sl->fscale = fs;
-                            sl->funit = 1.0 / fs;
-                        }
-                        bar_all();
+                        bar_all();  // the slot's fields (thread 0) are visible to everyone
                     }
                 }
                 if (sl->mode == 1) break;  // the prologue pass comes first
@@ -405,11 +435,19 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
                         }
                     tau = sqrt(bsum(part, red) / nd);  // (:203)
                     const double lt = sl->last_tau;
+                    if (D) bar_all();  // everyone has read last_tau before thread 0 overwrites it (FAST: bmax below)
                     // FAST stop rule of amp_kernel: tau jitters at the quantisation floor instead of reaching an exact
-                    // fp64 fixed point (:204), so stop once it moves by less than 2^-27 relative
-                    if (tau == lt || fabs(tau - lt) <= tau * 7.450580596923828e-09) {
+                    // fp64 fixed point (:204), so stop once it moves by less than 2^-27 relative; D: the reference's
+                    // exact-equality rule
+                    if (tau == lt || (!D && fabs(tau - lt) <= tau * 7.450580596923828e-09)) {
                         done = true;
                         if (tid == 0) sl->flags |= SB_AMP_STOPPED;
+                    } else if (D) {
+                        if (tid == 0) {
+                            sl->last_tau = tau;
+                            sl->tau2 = tau * tau;
+                            if (a.tau2_trace != nullptr) a.tau2_trace[(size_t)sl->b * a.T + sl->t] = tau * tau;
+                        }
                     } else {
                         const int ez = ceil_exp(bmax(zmax, red) * (1.0 + 1e-6));
                         const double zscale = scalbn(1.0, 27 - ez);
@@ -446,7 +484,7 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
             }
         }
         bar_all();
-        const int m0 = slot[0].active ? slot[0].mode : -1, m1 = slot[1].active ? slot[1].mode : -1;
+        const int m0 = slot[0].active ? slot[0].mode : -1, m1 = (!D && slot[1].active) ? slot[1].mode : -1;
         if (m0 < 0 && m1 < 0) break;
         const bool anyfold = (m0 == 0) || (m1 == 0);
 
@@ -465,8 +503,9 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
         }
 #endif
         if constexpr (OW) {
-            if (both) ow_pass<2>(a, n, G, rt, rw, q, zq, buf, anyfold, acc);
-            else ow_pass<1>(a, n, G, rt, rw, q, zq + (m0 >= 0 ? 0 : ZPLANE), buf + (m0 >= 0 ? 0 : CWOFF), anyfold, acc);
+            if constexpr (D) ow_pass<1, true, A>(a, n, G, rt, rw, q, zq, buf, anyfold, acc);
+            else if (both) ow_pass<2, false, A>(a, n, G, rt, rw, q, zq, buf, anyfold, acc);
+            else ow_pass<1, false, A>(a, n, G, rt, rw, q, zq + (m0 >= 0 ? 0 : ZPLANE), buf + (m0 >= 0 ? 0 : CWOFF), anyfold, acc);
         } else {
             bar_all();
             for (int i = 0; i < G; i++) {
@@ -478,11 +517,10 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
                     if (m1 == 0 && !slot[1].first_zero) prefetch_l2(a.beta + (size_t)slot[1].b * L * M + nxt);
                 }
 #pragma unroll TW_UNROLL
-                for (int c = 0; c < 2; c++) {  // (one copy of the transform code: instruction-cache footprint)
+                for (int c = 0; c < NSLOT; c++) {  // (one copy of the transform code: instruction-cache footprint)
                     if ((c ? m1 : m0) < 0) continue;
                     double dsq = 0.0, dmax = -INFINITY, dmin = INFINITY;
-                    transform_unit(a, slot + c, i * S + rw, q, reinterpret_cast<int *>(sec + c * CWOFF), Sp, Sn, rtp, inv_rt_n, dsq,
-                                   dmax, dmin);
+                    transform_unit<D>(a, slot + c, i * S + rw, q, sec + c * CWOFF, Sp, Sn, rtp, inv_rt_n, dsq, dmax, dmin);
                     if (c) { sq1 += dsq; gmax1 = fmax(gmax1, dmax); lmin1 = fmin(lmin1, dmin); }
                     else { sq0 += dsq; gmax0 = fmax(gmax0, dmax); lmin0 = fmin(lmin0, dmin); }
                 }
@@ -495,7 +533,7 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
 #endif
         // ---------------- end of pass: Onsager term and residual (sparc_ldpc.py:220), or z = y - A beta0 (:197-198)
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
+        for (int c = 0; c < NSLOT; c++) {
             const int mc = c ? m1 : m0;
             if (mc < 0) continue;
             Slot *sl = slot + c;
@@ -545,6 +583,7 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
     }
 }
 
+template <bool D>
 __global__ void __launch_bounds__(512, 1) amp2_kernel(Args a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, n = a.n, L = a.L;
@@ -553,7 +592,11 @@ __global__ void __launch_bounds__(512, 1) amp2_kernel(Args a) {
     Slot *slot = reinterpret_cast<Slot *>(red + 64);
     int *misc = reinterpret_cast<int *>(slot + 2);
     double *rtp = reinterpret_cast<double *>(misc + 16);
-    if (tid < 64) reinterpret_cast<int *>(zq + (tid >> 5) * ZPLANE)[n + (tid & 31)] = 0;  // one zero word per bank and plane
+    if (D) {
+        if (tid < 32) reinterpret_cast<double *>(zq)[n + tid] = 0.0;  // 32 zero words behind the fp64 plane
+    } else if (tid < 64) {
+        reinterpret_cast<int *>(zq + (tid >> 5) * ZPLANE)[n + (tid & 31)] = 0;  // one zero word per bank and plane
+    }
     if (tid < 2) {
         slot[tid].active = 0;
         slot[tid].mode = 0;
@@ -571,7 +614,7 @@ __global__ void __launch_bounds__(512, 1) amp2_kernel(Args a) {
     const double P = bsum(pl, red);  // np.sum(Pl) (:190)
     const double cmax = sqrt(nd * bmax(plmax, red));
     // |F| <= sqrt(n P_l) <= cmax; the 1e-6 margin keeps |F_q| strictly below 2^27 (sums of 8 terms stay in int32)
-    const double fscale_q = scalbn(1.0, 27 - ceil_exp(cmax * (1.0 + 1e-6)));
+    const double fscale_q = D ? 1.0 : scalbn(1.0, 27 - ceil_exp(cmax * (1.0 + 1e-6)));
     bar_all();
 #ifdef P2_DESYNC  // experiment: start the CTAs out of phase
     for (int i = 0; i < (int)(blockIdx.x % 37); i++) __nanosleep(20000);
@@ -581,12 +624,12 @@ __global__ void __launch_bounds__(512, 1) amp2_kernel(Args a) {
 #if P2_REGS_TW
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(256 - P2_REGS_TW));
 #endif
-        role_main<true>(a, smem, P, fscale_q);
+        role_main<true, D>(a, smem, P, fscale_q);
     } else {
 #if P2_REGS_TW
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P2_REGS_TW));
 #endif
-        role_main<false>(a, smem, P, fscale_q);
+        role_main<false, D>(a, smem, P, fscale_q);
     }
 }
 
@@ -608,7 +651,7 @@ extern "C" int sb_p2_trace_read(unsigned long long *out, int max_rows) {
 
 // FAST mode, all sections active, pair tables present.  scratch: [2][B][n] doubles (sb_amp_batch): the first
 // 2 * grid * n hold z of the resident slots, the work counter sits behind them when B > grid.
-int launch_amp2(const sb_operator *op, const AmpArgs &aa, int B, cudaStream_t st) {
+int launch_amp2(const sb_operator *op, const AmpArgs &aa, int B, int f64, cudaStream_t st) {
     static int nsm = 0;
     if (nsm == 0) {
         int dev = 0, v = 0;
@@ -618,7 +661,7 @@ int launch_amp2(const sb_operator *op, const AmpArgs &aa, int B, cudaStream_t st
     }
     p2::Args a;
     memset(&a, 0, sizeof(a));
-    a.inv2 = op->inv2; a.fwd2 = op->fwd2;
+    a.inv2 = f64 ? op->inv2d : op->inv2; a.fwd2 = f64 ? op->fwd2d : op->fwd2;
     a.y = aa.y; a.Pl = aa.Pl; a.beta0 = aa.beta0; a.beta = aa.beta; a.tau2_trace = aa.tau2_trace; a.zscratch = aa.zscratch;
     a.iters = aa.iters; a.n_exec = aa.n_exec; a.flags = aa.flags;
     a.L = op->L; a.n = op->n; a.T = aa.T; a.B = B;
@@ -629,8 +672,13 @@ int launch_amp2(const sb_operator *op, const AmpArgs &aa, int B, cudaStream_t st
     }
     const size_t smem = p2::smem_bytes(op->L);
     if (smem > 227 * 1024) return fail(SB_EINVAL, "AMP (pair kernel): L too large for shared memory%s (%ld bytes)", "", (long)smem);
-    SB_CUDA(cudaFuncSetAttribute(p2::amp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    p2::amp2_kernel<<<grid, 512, smem, st>>>(a);
+    if (f64) {
+        SB_CUDA(cudaFuncSetAttribute(p2::amp2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        p2::amp2_kernel<true><<<grid, 512, smem, st>>>(a);
+    } else {
+        SB_CUDA(cudaFuncSetAttribute(p2::amp2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        p2::amp2_kernel<false><<<grid, 512, smem, st>>>(a);
+    }
     SB_LAUNCHED();
     return SB_OK;
 }

@@ -103,6 +103,11 @@ struct sb_operator {
     int p2ok;
     uint16_t *inv2;       // [L][16][2 signs][32][8]  byte offset into one codeword's z plane [n | 32 zero words]
     uint16_t *fwd2;       // [L/8][n][8]              slot*4096 + word*4 | sign << 15 inside an 8-section group buffer
+    // SB_AMP_F64: the same two tables for 8-byte elements (k*8, slot*4096 + word*8), scheduled for half-warp pools of
+    // 16 lanes x 16 eight-byte banks; built on first use from h_ordering (p2d_state: 0 = not yet, 1 = ready, -1 = none)
+    uint16_t *inv2d, *fwd2d;
+    uint32_t *h_ordering;
+    int p2d_state;
 };
 
 struct sb_graph {

@@ -140,6 +140,11 @@ def test_pair_kernel_tables_are_a_reordering_of_the_operator(shape):
     rc = _lib.lib().sb_pair_tables_check(o.ctypes.data, L, M, n, st)
     assert rc == 0, _lib.lib().sb_last_error()
     assert st[0] > 0 and st[1] <= 1.3 * st[0] and st[3] <= 2.3 * st[2]
+    # the fp64 tables of SB_AMP_F64: the same terms, scheduled for half-warp pools of 16 lanes x 16 eight-byte banks
+    st2 = (ct.c_long * 4)()
+    rc = _lib.lib().sb_pair_tables_check_f64(o.ctypes.data, L, M, n, st2)
+    assert rc == 0, _lib.lib().sb_last_error()
+    assert st2[0] == 2 * st[0] and st2[1] <= 1.3 * st2[0] and st2[3] <= 2.3 * st2[2]
     for L2, M2, n2 in ((20, 512, 180), (64, 256, 576), (16, 512, 6000)):   # L % 8, M != 512, w/M = 32
         o2 = make_ordering(L2, M2, n2)
         assert _lib.lib().sb_pair_tables_check(o2.ctypes.data, L2, M2, n2, None) == 1
