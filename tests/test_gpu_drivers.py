@@ -310,3 +310,26 @@ def test_parity_mode_drivers_sharded_over_two_ranks():
     assert {d["driver"] for d in lines} >= {"waterfall_soft", "waterfall_originalHard", "soft_hard_plot", "soft_hardinit_plot",
                                             "sim_ldpc", "amp_exit_curve"}
     assert all(d["identical_on_all_ranks"] for d in lines)
+
+
+def test_cliff_point_modes_and_reference_stream(oracle):
+    """The bench's operating point (7.667 ref-dB, on the cliff of the waterfall), tools/cliff_point.py at a test-sized
+    sample: (A) the same device-generated codewords in strict / f64 / fast mode -- decisions of converged codewords
+    identical; (B) codewords from the reference's RNG stream through the CPU oracle and the GPU -- per-codeword BER
+    tuples identical outside the documented non-convergent classes.  The full-size run (4736 + 256 codewords) is
+    profiles/r02_cliff_point.json."""
+    import importlib.util
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("cliff_point", os.path.join(ROOT, "tools", "cliff_point.py"))
+    cp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cp)
+    a = cp.part_a(296)
+    print({k: v["block_failures_per_stage"] for k, v in a["modes"].items()}, a["comparison"])
+    assert a["ok"]
+    for v in a["comparison"].values():
+        assert v["converged_codewords"] >= 148
+    b = cp.part_b(int(os.environ.get("SPARC_B200_CLIFF_K", "16")))
+    print({k: (v["identical_tuples"], v["different"], v["unexplained"]) for k, v in b["modes"].items()})
+    assert b["ok"]
+    for v in b["modes"].values():
+        assert v["identical_tuples"] >= 0.6 * b["codewords"]
