@@ -101,7 +101,11 @@ __host__ __device__ inline size_t smem_bytes(int L) {
 }
 
 __device__ __forceinline__ void bar_all() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+#ifdef P2_NO_BAR_OW  // timing experiment only (racy): upper bound of what a third group buffer could win
+__device__ __forceinline__ void bar_ow() {}
+#else
 __device__ __forceinline__ void bar_ow() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+#endif
 
 // deterministic CTA-wide reductions over all 16 warps (every thread adds the warp partials in warp order)
 __device__ __forceinline__ double bsum(double v, double *scratch) {

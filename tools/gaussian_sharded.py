@@ -90,14 +90,18 @@ if args.check and world > 1:
     b = op.amp_p2p(y, Pl_loc, args.P, args.T, peers)
     c = op.amp_p2p(y, Pl_loc, args.P, args.T, peers)
     torch.cuda.synchronize()
-    same = torch.equal(b.beta, c.beta) and torch.equal(a.iters, b.iters) and torch.equal(a.n_exec, b.n_exec)
+    same = torch.equal(b.beta, c.beta) and torch.equal(b.iters, c.iters)          # the peer exchange is repeatable bit for bit
     rel = float((a.beta - b.beta).abs().max() / a.beta.abs().max())
-    # the all-reduce adds the ranks' partial sums in the library's order, the peer exchange in rank order
-    ok = torch.tensor([1.0 if (same and rel < 1e-9) else 0.0], dtype=torch.float64, device="cuda")
+    dit = int((a.n_exec - b.n_exec).abs().max())
+    # The all-reduce adds the ranks' partial sums in the library's order (a tree / NVLS at 8 ranks), the peer exchange in
+    # rank order: identical for 2 ranks, fp64 rounding apart beyond.  The tolerance stop |d tau| <= 2^-27 tau is then a
+    # near-tie: a codeword may stop one iteration apart, and beta differs by that iteration's (converged) step.
+    ok_flag = same and ((rel < 1e-9 and dit == 0) or (rel < 1e-6 and dit <= 1))
+    ok = torch.tensor([1.0 if ok_flag else 0.0], dtype=torch.float64, device="cuda")
     allreduce_any(ok, dist.ReduceOp.MIN)
     if rank == 0:
-        print("check: peer-memory exchange vs all-reduce: max rel beta difference %.2e, iterations %s, repeatable %s -> %s"
-              % (rel, b.iters[:4].tolist(), same, "OK" if float(ok) == 1.0 else "MISMATCH"))
+        print("check: peer-memory exchange vs all-reduce: max rel beta difference %.2e, iterations %s (max difference %d), "
+              "repeatable %s -> %s" % (rel, b.iters[:4].tolist(), dit, same, "OK" if float(ok) == 1.0 else "MISMATCH"))
     if float(ok) != 1.0:
         sys.exit(1)
 for rep in range(args.reps):
@@ -136,6 +140,7 @@ if rank == 0 and args.json:
     import json
     if args.check and world > 1:
         last["peer_memory_vs_allreduce_max_rel_beta_diff"] = rel
+        last["peer_memory_vs_allreduce_max_iteration_difference"] = dit
         last["peer_memory_repeatable_bitwise"] = bool(same)
     with open(args.json, "w") as fh:
         json.dump(last, fh, indent=1)
