@@ -482,7 +482,9 @@ def gpu_arm(args):
                 c = cpu_run(1, 0)
                 line["cpu_baseline"] = {"value": c["value"], "unit": "codewords/s", "cores": c["cores"], "kind": "port",
                                         "sample": "1 soft-flow codeword per worker on %d workers (%.1f s per codeword per core); "
-                                                  "oracle port of the reference algorithm" % (c["cores"], c["per_codeword_s"])}
+                                                  "oracle port of the reference algorithm; the unmodified reference needs 2.7x the "
+                                                  "port's time for the same codeword with identical BER tuples (build container, "
+                                                  "one core each: profiles/r02_port_vs_reference.json)" % (c["cores"], c["per_codeword_s"])}
             except Exception as ex:  # the baseline is reported, never the product path
                 line["cpu_baseline"] = {"value": None, "unit": "codewords/s", "cores": 0, "kind": "port", "sample": "failed: %r" % ex}
         print(json.dumps(line))

@@ -666,7 +666,10 @@ static int dense_gemm_launch(const sb_dense *d, int transpose, const __nv_bfloat
     const int Mrows = transpose ? d->LM : d->n, K = transpose ? d->n : d->LM, Kp = transpose ? d->np : d->LMp;
     const int BN = pick_bn(B);
     const int mtiles = (Mrows + GM - 1) / GM;
-    int CL = 2;  // cluster size: the codeword-side tile is fetched once per cluster (SB_DENSE_CLUSTER = 1 | 2 | 4)
+    // cluster size: the codeword-side tile is fetched once per cluster (SB_DENSE_CLUSTER = 1 | 2 | 4).  Measured at n = 4608,
+    // LM = 65536, B = 256 (tools/r2_dense.sh): A beta (36 row tiles) 0.89 ms with 2, 1.17 ms with 4; A^T z (512 row tiles)
+    // 0.99 ms with 2, 0.95 ms with 4
+    int CL = transpose ? 4 : 2;
     if (const char *env = knob("SB_DENSE_CLUSTER")) CL = atoi(env);
     if (CL != 1 && CL != 2 && CL != 4) CL = 2;
     while (CL > 1 && mtiles < CL) CL /= 2;
