@@ -130,7 +130,10 @@ int sb_onehot_apply_batch(const sb_operator *op, const int *idx, const double *P
  *   sections[B][L] / nsec[B] or NULL (all sections): active-section lists, beta is compact;
  *   beta[B][L*M] out; iters[B] out = the `t` amp_test returns; n_exec[B] out = iterations
  *   actually executed; flags[B] out (SB_AMP_*); tau2_trace[B][T] or NULL. */
-#define SB_AMP_STRICT 0 /* fp64 everywhere, reference order of additions: A beta / A^T z bit-identical           */
+#define SB_AMP_STRICT 0 /* fp64 everywhere; the two operator products inside the loop add in the reference's order (the
+                           kernels behind sb_Ab_batch / sb_Az_batch, which ARE bit-identical to the reference).  The decode as a
+                           whole is not bit-faithful -- section maximum instead of the global one, multiplication by 1/sqrt(n),
+                           CUDA's exp, FMA contraction -- and agrees with the reference to ~1e-12 per iteration              */
 #define SB_AMP_FAST 1   /* z and FHT(beta) are gathered from 32-bit fixed-point copies (27 bits below their
                            power-of-two ceiling), adds of the two gathers are exact integer adds; FHT, softmax,
                            z update and tau^2 stay fp64.  beta / tau^2 agree with STRICT to ~1e-8 relative.  The
