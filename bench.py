@@ -449,8 +449,10 @@ def gpu_arm(args):
         }
         line["roofline"]["co_limiter"] = (
             "not HBM: the L1 / shared-memory data pipe (2 L n random shared-memory reads per codeword-iteration + the "
-            "L2-resident table words) -- ncu l1tex__data_pipe_lsu_wavefronts 78 % of peak, dram/algorithmic bytes 0.93 "
-            "(profiles/r02_amp_kernel_ncu_full.csv)")
+            "L2-resident table words).  ncu of this build: l1tex__data_pipe_lsu_wavefronts 81 % of peak (F64 kernel 91 %, "
+            "STRICT 85 % with half of its wavefronts bank conflicts), dram / algorithmic bytes 0.92; as a roofline of that "
+            "pipe: 532 k wavefronts per codeword-iteration at 1 per cycle and SM = 1.84 us, measured 2.31 in an isolated "
+            "launch (profiles/r02_amp_kernel_ncu_full.csv, r02_amp2_hotspots.txt, DESIGN.md section 6b)")
         def ref_record(rec, amp_key):
             return {
                 "what": "the same step with amp %s + bp strict, %d timed step(s) after 1 warm-up step on %d codewords"

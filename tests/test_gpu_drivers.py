@@ -318,11 +318,12 @@ def test_cliff_point_modes_and_reference_stream(oracle):
     identical; (B) codewords from the reference's RNG stream through the CPU oracle and the GPU -- per-codeword BER
     tuples identical outside the documented non-convergent classes.  The full-size run (4736 + 256 codewords) is
     profiles/r02_cliff_point.json."""
-    import importlib.util
+    import sys
     from conftest import ROOT
-    spec = importlib.util.spec_from_file_location("cliff_point", os.path.join(ROOT, "tools", "cliff_point.py"))
-    cp = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(cp)
+    tools = os.path.join(ROOT, "tools")
+    if tools not in sys.path:
+        sys.path.insert(0, tools)          # (a plain import: the oracle workers unpickle cliff_point._oracle_one by name)
+    import cliff_point as cp
     a = cp.part_a(296)
     print({k: v["block_failures_per_stage"] for k, v in a["modes"].items()}, a["comparison"])
     assert a["ok"]
