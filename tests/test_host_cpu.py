@@ -148,3 +148,55 @@ def test_pair_kernel_tables_are_a_reordering_of_the_operator(shape):
     for L2, M2, n2 in ((20, 512, 180), (64, 256, 576), (16, 512, 6000)):   # L % 8, M != 512, w/M = 32
         o2 = make_ordering(L2, M2, n2)
         assert _lib.lib().sb_pair_tables_check(o2.ctypes.data, L2, M2, n2, None) == 1
+
+
+def test_bench_helpers_without_a_gpu():
+    """bench.py / tools used by it, host logic only: the union of overlapping launch intervals, the exponential power
+    allocation of the C2 shape (waterfall(pa_param=True): a = f = r / C from the first grid point, sparc_ldpc.py:1201-1204),
+    and the acceptance rule of the cliff-point comparison."""
+    import importlib.util
+    import sys
+    from conftest import ROOT
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    bench = load("bench_mod", os.path.join(ROOT, "bench.py"))
+
+    class Ev:                                   # stands in for torch.cuda.Event: elapsed_time in ms
+        def __init__(self, t):
+            self.t = t
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+
+    e0 = Ev(0.0)
+    pairs = [(Ev(1.0), Ev(4.0)), (Ev(3.0), Ev(6.0)), (Ev(10.0), Ev(11.0)), (Ev(10.5), Ev(10.75))]
+    assert bench._union_ms(e0, pairs) == pytest.approx(6.0)
+    assert bench._union_ms(e0, []) == 0.0
+    assert bench.N == 4608 and bench.INFO_BITS == 3840 and abs(bench.SIGMA - 0.9963928922771221) < 1e-15
+
+    shapes = load("bench_shapes_mod", os.path.join(ROOT, "tools", "bench_shapes.py"))
+    pa = shapes.pa_exponential(512, 4.0, 1.0, 5.2)
+    s0 = np.sqrt(4.0 / (10 ** (5.2 / 20) * 2 * 1.0))
+    C = 0.5 * np.log2(1 + 4.0 / s0 ** 2)
+    assert pa["C"] == pytest.approx(C) and pa["a"] == pytest.approx(1.0 / C) and pa["f"] == pa["a"] and pa["f"] < 1.0
+    from sparc_ldpc_b200.sparc_ldpc import pa_parameterised
+    Pl = pa_parameterised(512, pa["C"], 4.0, pa["a"], pa["f"])
+    assert Pl.sum() == pytest.approx(4.0) and 3.0 < Pl[0] / Pl[-1] < 4.0 and np.all(np.diff(Pl) <= 1e-15)   # decaying, flat tail
+    assert np.all(Pl[int(pa["f"] * 512):] == Pl[-1])
+
+    cliff = load("cliff_point", os.path.join(ROOT, "tools", "cliff_point.py"))
+    good = {"f64_vs_strict": {"converged_codewords": 3520, "converged_with_identical_decisions": 3520},
+            "fast_vs_strict": {"converged_codewords": 3520, "converged_with_identical_decisions": 3519}}
+    assert cliff.part_a_ok(good) and good["fast_vs_strict"]["near_tie_flips_among_converged"] == 1
+    bad = {"f64_vs_strict": {"converged_codewords": 3520, "converged_with_identical_decisions": 3519},
+           "fast_vs_strict": {"converged_codewords": 3520, "converged_with_identical_decisions": 3520}}
+    assert not cliff.part_a_ok(bad)
+    worse = {"f64_vs_strict": {"converged_codewords": 3520, "converged_with_identical_decisions": 3520},
+             "fast_vs_strict": {"converged_codewords": 3520, "converged_with_identical_decisions": 3400}}
+    assert not cliff.part_a_ok(worse)
