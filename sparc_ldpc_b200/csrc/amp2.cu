@@ -297,7 +297,8 @@ __device__ __forceinline__ void transform_unit(const Args &a, const Slot *sl, in
         double sum = 0.0;
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            x[e] = exp(x[e] - m);  // section max instead of the reference's global max (:216): same softmax
+            // section max instead of the reference's global max (:216): same softmax
+            x[e] = (!D && SB_FAST_EXP) ? exp_nonpos(x[e] - m) : exp(x[e] - m);
             sum += x[e];
         }
 #pragma unroll
