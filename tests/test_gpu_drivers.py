@@ -334,3 +334,19 @@ def test_cliff_point_modes_and_reference_stream(oracle):
     assert b["ok"]
     for v in b["modes"].values():
         assert v["identical_tuples"] >= 0.6 * b["codewords"]
+
+
+def test_notebook_amp_sim_known_answer():
+    """sparc_amp.ipynb cell 21: np.random.seed(0); amp_sim(1024, 512, 1.0, 15.0, 1.4, 64, 1.4) -> n = 6582, fc = 1.0,
+    ber = 0.0, ser = 0.0, C = 2.0, EbN0 = 5.357142857142858, snr = 15.0 (the notebook's recorded output), and the
+    bitwise-posterior known answer of cell 25."""
+    from sparc_ldpc_b200 import sparc_amp as SA
+    np.random.seed(0)
+    rec = SA.amp_sim(1024, 512, 1.0, 15.0, 1.4, 64, 1.4, full=True)
+    want = {"C": 2.0, "EbN0": 5.357142857142858, "L": 1024, "M": 512, "P": 15.0, "R": 1.4, "R_PA": 1.4, "T": 64, "ber": 0.0,
+            "fc": 1.0, "n": 6582, "ser": 0.0, "sigma_n": 1.0, "snr": 15.0}
+    assert rec == want, rec
+    np.random.seed(0)
+    assert SA.amp_sim(1024, 512, 1.0, 15.0, 1.4, 64, 1.4, mode="fast") == 0.0
+    beta = np.array([0.7, 0.3, 0.6, 0.4, 0.4, 1.6, 0.4, 0.3])
+    np.testing.assert_allclose(SA.bitwise_posterior(beta, 2, 4), [0.5, 0.35, 0.25925926, 0.7037037], rtol=0, atol=5e-9)

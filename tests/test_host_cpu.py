@@ -200,3 +200,20 @@ def test_bench_helpers_without_a_gpu():
     worse = {"f64_vs_strict": {"converged_codewords": 3520, "converged_with_identical_decisions": 3520},
              "fast_vs_strict": {"converged_codewords": 3520, "converged_with_identical_decisions": 3400}}
     assert not cliff.part_a_ok(worse)
+
+
+def test_notebook_power_allocations():
+    """sparc_amp.ipynb cells 9 / 13 (host functions of sparc_ldpc_b200.sparc_amp): sums, shapes, and the iterative
+    allocation of the notebook's recorded run (L = 1024, sigma = 1, P = 15, R_PA = 1.4: blocks of one section)."""
+    from sparc_ldpc_b200 import sparc_amp as SA
+    pa = SA.pa_original(64, 1.5, 7.0)
+    assert pa.sum() == pytest.approx(7.0) and np.all(np.diff(pa) < 0) and pa[0] / pa[-1] == pytest.approx(2 ** (2 * 1.5 * 63 / 64))
+    PA = SA.pa_iterative(1024, 1024, 1.0, 15.0, 1.4)
+    assert PA.sum() == pytest.approx(15.0) and np.all(np.diff(PA) <= 1e-18) and PA[-1] > 0
+    # first section: P_block = 2 ln 2 (R_PA / L) (sigma^2 + P)
+    assert PA[0] == pytest.approx(2 * np.log(2) * (1.4 / 1024) * 16.0)
+    flat = np.flatnonzero(PA == PA[-1])
+    assert 0 < flat[0] < 1024 and np.all(PA[flat[0]:] == PA[-1])          # the tail is spread evenly
+    # with B < L the blocks are L // B sections wide
+    PB = SA.pa_iterative(16, 4, 1.0, 15.0, 1.0)
+    assert PB.sum() == pytest.approx(15.0) and PB[0] == PB[3]
