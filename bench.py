@@ -505,7 +505,10 @@ def main():
                          "+6 %%, +1.3 %%)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--streams", type=int, default=8, help="slices of the batch decoded on concurrent CUDA streams")
+    ap.add_argument("--streams", type=int, default=4,
+                    help="slices of the batch decoded on concurrent CUDA streams (round-2 sweep at batch 9472: 2 / 3 / 4 / 8 / 16 "
+                         "streams -> 6061 / 6071 / 6090 / 6039 / 5935 codewords/s: longer launches keep both slots of the pair "
+                         "kernel's CTAs filled, a few slices still hide the launches' tails)")
     ap.add_argument("--no-strict", action="store_true", help="skip the strict/strict record")
     ap.add_argument("--strict-steps", type=int, default=1, help="timed steps of the strict/strict record")
     ap.add_argument("--no-shapes", action="store_true", help="skip the per-shape block (BASELINE.json configs)")
