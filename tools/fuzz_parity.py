@@ -1,5 +1,5 @@
-"""Randomised parity sweep (test infrastructure): random (L, M, rate, power allocation, noise) -> the CUDA AMP in STRICT
-and FAST mode against the CPU oracle on the same codeword.  Reports the worst deviations; exits non-zero when a
+"""Randomised parity sweep (test infrastructure): random (L, M, rate, power allocation, noise) -> the CUDA AMP in STRICT,
+F64 and FAST mode against the CPU oracle on the same codeword.  Reports the worst deviations; exits non-zero when a
 tolerance of the parity tests is exceeded.   python tools/fuzz_parity.py [--cases 60] [--seed 1]"""
 import argparse
 import os
@@ -20,7 +20,7 @@ ap.add_argument("--seed", type=int, default=1)
 ap.add_argument("--budget-s", type=float, default=150.0)
 args = ap.parse_args()
 rs = np.random.RandomState(args.seed)
-worst = {"strict_beta": 0.0, "fast_beta": 0.0}
+worst = {"strict_beta": 0.0, "f64_beta": 0.0, "fast_beta": 0.0}
 bad, notes, t0, done, n_refnan, n_chaotic, n_early = [], [], time.time(), 0, 0, 0, 0
 for case in range(args.cases):
     if time.time() - t0 > args.budget_s:
@@ -53,7 +53,7 @@ for case in range(args.cases):
     Pld = torch.from_numpy(Pl).cuda()
     b0d = torch.from_numpy(prior.reshape(1, -1)).cuda() if with_prior else None
     scale = np.max(np.abs(ref)) or 1.0
-    for mode, tol in (("strict", 1e-9), ("fast", 2e-6)):
+    for mode, tol in (("strict", 1e-9), ("f64", 1e-9), ("fast", 2e-6)):   # (f64 differs from strict only at M = 512)
         res = op.amp(yd, Pld, T, beta0=b0d, trace=True, mode=mode)
         beta = res.beta.cpu().numpy().reshape(-1)
         it_ref, it = int(t_ref), int(res.iters[0])
@@ -93,9 +93,9 @@ for case in range(args.cases):
             eb = ek
         bad.append((case, mode, L, M, n, T, with_prior, eb, it, it_ref))
     done += 1
-print("fuzz: %d cases in %.0f s, worst relative beta error strict %.2e fast %.2e; %d reference-underflow cases skipped, "
+print("fuzz: %d cases in %.0f s, worst relative beta error strict %.2e f64 %.2e fast %.2e; %d reference-underflow cases skipped, "
       "%d non-convergent FAST cases checked after 8 iterations, %d early FAST stops checked at equal iteration count"
-      % (done, time.time() - t0, worst["strict_beta"], worst["fast_beta"], n_refnan, n_chaotic, n_early))
+      % (done, time.time() - t0, worst["strict_beta"], worst["f64_beta"], worst["fast_beta"], n_refnan, n_chaotic, n_early))
 for m in [x for x in notes if x.startswith("early")][:4] + [x for x in notes if not x.startswith("early")][:3]:
     print("  " + m)
 for b in bad:
