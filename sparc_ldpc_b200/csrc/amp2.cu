@@ -320,14 +320,25 @@ __device__ __forceinline__ void transform_unit(const Args &a, const Slot *sl, in
             bdst[e * 32 + q] = x[e];
         }
     }
-    fht512_A_to_B(x, q, Sp, Sn);
     if constexpr (D) {
+        fht512_A_to_B(x, q, Sp, Sn);
 #pragma unroll
         for (int e = 0; e < 16; e++) std_[e * 32 + q] = x[e];  // word e*32+q = fq_word(lo)
     } else {
+#if SB_INT_FHT2  // exact 32-bit fixed-point transform of the 30-bit quantised beta (amp_impl.cuh), F rounded to 27 bits
+        int xi[16];
+        const double fs30 = sl->fscale * 8.0;
+#pragma unroll
+        for (int e = 0; e < 16; e++) xi[e] = __double2int_rn(x[e] * fs30);
+        fht512_A_to_B_i(xi, q, Sp);
+#pragma unroll
+        for (int e = 0; e < 16; e++) st[e * 32 + q] = (xi[e] + 4) >> 3;  // word e*32+q = fq_word(lo)
+#else
+        fht512_A_to_B(x, q, Sp, Sn);
         const double fs = sl->fscale;
 #pragma unroll
         for (int e = 0; e < 16; e++) st[e * 32 + q] = __double2int_rn(x[e] * fs);  // word e*32+q = fq_word(lo)
+#endif
     }
 }
 

@@ -156,6 +156,50 @@ __device__ __forceinline__ void fht512_A_to_B(double (&x)[16], int q, int *Fp, i
     shuffle_stage1(x, q);
 }
 
+// ---- FAST mode: the SECOND transform (beta_l -> F_l) in exact 32-bit fixed point ---------------------------------
+// beta_l >= 0 sums to sqrt(n P_l) <= cmax, so with beta quantised to 30 bits below the power-of-two ceiling of cmax every
+// butterfly value is bounded by sum_j beta_q[j] < 2^31: the integer transform is exact, its transpose moves 4-byte words
+// (32 shared-memory wavefronts instead of 64) and its shuffle stage one register per element instead of two.  F is then
+// rounded from 30 to the 27 bits the gathers use.  Error of F in units of 2^-27 cmax: 0.8 rms (512 rounded inputs) instead
+// of 0.3 (one rounding) -- two orders of magnitude inside FAST's tolerance.  In the alternating-phase kernel of round 1
+// this variant lost (the integer pipe was the busier one); with the transform warps on their own it wins.
+#ifndef SB_INT_FHT2
+#define SB_INT_FHT2 1
+#endif
+__device__ __forceinline__ int *stage_at_i(int *base, int row, int col) { return base + row * 32 + (col ^ ((2 * row) & 31)); }
+
+__device__ __forceinline__ void reg_stages16_i(int (&x)[16]) {
+#pragma unroll
+    for (int s = 8; s >= 1; s >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if ((i & s) == 0) {
+                const int a = x[i], b = x[i + s];
+                x[i] = a + b;
+                x[i + s] = a - b;
+            }
+        }
+    }
+}
+
+// layout A in, layout B out (as fht512_A_to_B); S: 2 KB of the warp's own shared memory
+__device__ __forceinline__ void fht512_A_to_B_i(int (&x)[16], int q, int *S) {
+    reg_stages16_i(x);
+#pragma unroll
+    for (int i = 0; i < 16; i++) *stage_at_i(S, i, q) = x[i];
+    __syncwarp();
+    const int a = q >> 1, b = q & 1;
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = *stage_at_i(S, a, 2 * i + b);
+    __syncwarp();
+    reg_stages16_i(x);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int p = __shfl_xor_sync(0xffffffffu, x[i], 1);
+        x[i] = b ? p - x[i] : p + x[i];
+    }
+}
+
 // physical word of F_l[lo] inside its +-F copy (FAST mode, M = 512): the transform ends in layout B, and
 // p(lo) = ((lo >> 1) & 15) * 32 + (lo >> 5) * 2 + (lo & 1) makes the store of register i a contiguous 128 bytes
 __host__ __device__ __forceinline__ uint32_t fq_word(int logM, uint32_t lo) {
@@ -446,6 +490,19 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
         }
     }
     if constexpr (TRQ) {
+#if SB_INT_FHT2
+        int xi[EPT];
+        const double fs30 = cx.fscale * 8.0;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) xi[e] = __double2int_rn(x[e] * fs30);
+        fht512_A_to_B_i(xi, q, Fqp);
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {  // register e of lane q holds lo = (q>>1)*32 + 2e + (q&1): word e*32 + q
+            const int f = (xi[e] + 4) >> 3;
+            Fqp[e * 32 + q] = f;
+            Fqn[e * 32 + q] = -f;
+        }
+#else
         fht512_A_to_B(x, q, Fqp, Fqn);
 #pragma unroll
         for (int e = 0; e < EPT; e++) {  // register e of lane q holds lo = (q>>1)*32 + 2e + (q&1): word e*32 + q
@@ -453,6 +510,7 @@ __device__ __forceinline__ void section_phase(int mode, bool first_zero, const A
             Fqp[e * 32 + q] = f;
             Fqn[e * 32 + q] = -f;
         }
+#endif
         SB_CLK(a, 4);
         return;
     }
