@@ -1,4 +1,5 @@
-// amp2.cu -- FAST-mode AMP decoder for M = 512, two codewords per CTA, warp-specialised (sm_100a).
+// amp2.cu -- AMP decoder for M = 512, warp-specialised (sm_100a): FAST mode with two codewords per CTA
+// (amp2_kernel<false>) and F64 mode with one fp64 codeword per CTA (amp2_kernel<true>, SB_AMP_F64).
 //
 // Same arithmetic as amp_kernel<9, *, QUANT> of amp_impl.cuh (ldpc/sparc_ldpc.py:189-222 over the operator of
 // :32-147; fp64 transforms / softmax / z update / tau^2, 27-bit fixed-point gathers), re-organised around what
@@ -24,6 +25,13 @@
 // Slots are refilled from a per-launch work counter as soon as a codeword stops, so a codeword that runs all T
 // iterations never idles its partner.  Integer gathers are order-free, hence A^T z and A beta are bit-identical to
 // amp_kernel's FAST path; tau^2 and |beta|^2 are summed over a different thread partition (last-bit differences).
+// Both FAST kernels run the second transform (beta_l -> F_l) in exact 32-bit fixed point and use exp_nonpos
+// (amp_impl.cuh).
+//
+// F64 (template parameter D): the same structure on fp64 values -- ONE codeword per CTA (its fp64 z plane takes the room
+// of the two int32 planes, a group buffer is [8][512] doubles), LDS.64 gathers through tables scheduled for half-warp
+// pools (amp.cu, build_pair_tables(f64 = 1)), A beta in fp64 registers, the reference's exact-equality stop rule, no
+// quantisation.  It differs from the order-preserving STRICT kernel by fp64 summation-order noise only.
 #include "amp_impl.cuh"
 
 #include <type_traits>
