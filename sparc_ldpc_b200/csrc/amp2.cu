@@ -450,13 +450,22 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
                 bool done = sl->t >= a.T;
                 double tau = 0.0;
                 if (!done) {
-                    double part = 0.0, zmax = 0.0;
-                    if (OW)
-                        for (int k = rt; k < n; k += NOW) {
-                            const double v = zc[k];
-                            part += v * v;
-                            zmax = fmax(zmax, fabs(v));
+                    // the thread's rows of z, all loads in flight together (FAST: z lives in global scratch; a rolled loop
+                    // exposed one L2 round trip per row, twice per slot: 19 -> 12 us per iteration boundary) and kept
+                    // for the fixed-point copy below (the accumulator registers are dead here)
+                    double part = 0.0, zmax = 0.0, zv[NR];
+                    if (OW) {
+#pragma unroll
+                        for (int j = 0; j < NR; j++) {
+                            const int k = rt + NOW * j;
+                            zv[j] = (k < n) ? zc[k] : 0.0;
                         }
+#pragma unroll
+                        for (int j = 0; j < NR; j++) {
+                            part += zv[j] * zv[j];
+                            zmax = fmax(zmax, fabs(zv[j]));
+                        }
+                    }
                     tau = sqrt(bsum(part, red) / nd);  // (:203)
                     const double lt = sl->last_tau;
                     if (D) bar_all();  // everyone has read last_tau before thread 0 overwrites it (FAST: bmax below)
@@ -483,7 +492,11 @@ __device__ __forceinline__ void role_main(const Args &a, unsigned char *smem, co
                         }
                         if (OW) {
                             int *zp = reinterpret_cast<int *>(zq + c * ZPLANE);
-                            for (int k = rt; k < n; k += NOW) zp[k] = __double2int_rn(zc[k] * zscale);
+#pragma unroll
+                            for (int j = 0; j < NR; j++) {
+                                const int k = rt + NOW * j;
+                                if (k < n) zp[k] = __double2int_rn(zv[j] * zscale);
+                            }
                         }
                     }
                 }
