@@ -535,10 +535,16 @@ static int ensure_f64_tables(sb_operator *op) {
     PairTables pt;
     build_pair_tables(op->h_ordering, op->L, op->M, op->n, op->H, pt, 1);
     if (!pt.ok) { op->p2d_state = -1; return 1; }
-    SB_CUDA(cudaMalloc(&op->inv2d, pt.inv2.size() * 2));
-    SB_CUDA(cudaMalloc(&op->fwd2d, pt.fwd2.size() * 2));
-    SB_CUDA(cudaMemcpy(op->inv2d, pt.inv2.data(), pt.inv2.size() * 2, cudaMemcpyHostToDevice));
-    SB_CUDA(cudaMemcpy(op->fwd2d, pt.fwd2.data(), pt.fwd2.size() * 2, cudaMemcpyHostToDevice));
+    cudaError_t e1 = cudaMalloc(&op->inv2d, pt.inv2.size() * 2), e2 = cudaMalloc(&op->fwd2d, pt.fwd2.size() * 2);
+    if (e1 == cudaSuccess) e1 = cudaMemcpy(op->inv2d, pt.inv2.data(), pt.inv2.size() * 2, cudaMemcpyHostToDevice);
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(op->fwd2d, pt.fwd2.data(), pt.fwd2.size() * 2, cudaMemcpyHostToDevice);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {  // no tables: this and later F64 calls run the STRICT kernel
+        cudaFree(op->inv2d); cudaFree(op->fwd2d);
+        op->inv2d = nullptr; op->fwd2d = nullptr;
+        op->p2d_state = -1;
+        (void)cudaGetLastError();
+        return 1;
+    }
     free(op->h_ordering);
     op->h_ordering = nullptr;
     op->p2d_state = 1;
