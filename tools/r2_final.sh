@@ -14,4 +14,4 @@ for k in ("f64","strict"):
 print(d.get("speedup_vs_strict")); print(d.get("roofline_bp",{}).get("frac"), d.get("cpu_baseline",{}).get("value"))
 for s in d.get("shapes",[]): print(s.get("shape"), s.get("codewords_per_s"), s.get("us_per_codeword_iteration"), s.get("frac"))
 P
-bash tools/r2_ncu_one.sh final
+# (ncu capture: tools/r2_ncu_one.sh final)
